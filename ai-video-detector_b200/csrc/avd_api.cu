@@ -1,0 +1,371 @@
+// C ABI of libavd.so (include/avd.h): context, resampling tables, entry points, host streaming pipeline.
+#include "avd_internal.h"
+#include <math.h>
+#include <string.h>
+#include <stdio.h>
+#include <new>
+#include <vector>
+
+static_assert(sizeof(avd_sample_rec) == 160, "record layout is part of the ABI");
+
+// ---- resampling tables (host) ------------------------------------------------------------------------
+// INTER_AREA decimation cells (video.py:6): restated from the library's table builder, SURVEY.md A.2.
+static void build_area_cells(int ssize, int dsize, AreaCell *cells)
+{
+    double scale = (double)ssize / dsize;
+    for (int d = 0; d < dsize; d++) {
+        double fs1 = d * scale, fs2 = fs1 + scale;
+        double cell = scale < (ssize - fs1) ? scale : (ssize - fs1);
+        int s1 = (int)ceil(fs1), s2 = (int)floor(fs2);
+        if (s2 > ssize - 1) s2 = ssize - 1;
+        if (s1 > s2) s1 = s2;
+        AreaCell c{};
+        c.s1 = s1; c.s2 = s2;
+        c.has_head = (s1 - fs1 > 1e-3);
+        c.ah = c.has_head ? (float)((s1 - fs1) / cell) : 0.f;
+        c.am = (float)(1.0 / cell);
+        c.has_tail = (fs2 - s2 > 1e-3);
+        if (c.has_tail) {
+            double t = fs2 - s2;
+            if (t > 1.0) t = 1.0;
+            if (t > cell) t = cell;
+            c.at = (float)(t / cell);
+        }
+        cells[d] = c;
+    }
+}
+
+// INTER_LINEAR 8-bit taps (video.py:43): SURVEY.md A.3.
+static void build_lin_taps(int ssize, int dsize, LinTap *taps, bool is_y)
+{
+    double scale = 1.0 / ((double)dsize / ssize);
+    for (int d = 0; d < dsize; d++) {
+        float f = (float)((d + 0.5) * scale - 0.5);
+        int s = (int)floorf(f);
+        f -= (float)s;
+        LinTap t{};
+        if (!is_y) {
+            if (s < 0) { f = 0.f; s = 0; }
+            if (s >= ssize - 1) { f = 0.f; s = ssize - 1; }
+            t.i0 = s; t.i1 = s + 1 < ssize ? s + 1 : ssize - 1;
+        } else {
+            t.i0 = s < 0 ? 0 : (s >= ssize ? ssize - 1 : s);
+            t.i1 = s + 1 < 0 ? 0 : (s + 1 >= ssize ? ssize - 1 : s + 1);
+        }
+        t.a0 = (int)lrintf((1.f - f) * 2048.f);
+        t.a1 = (int)lrintf(f * 2048.f);
+        taps[d] = t;
+    }
+}
+
+int avd_get_tables(avd_ctx *ctx, int H, int W, const ShapeTables **dev, const ShapeTables **host)
+{
+    auto key = std::make_pair(H, W);
+    auto it = ctx->tables.find(key);
+    if (it == ctx->tables.end()) {
+        ShapeTables t{};
+        build_area_cells(W, AVD_D, t.ax);
+        build_area_cells(H, AVD_D, t.ay);
+        build_lin_taps(W, AVD_T, t.lx, false);
+        build_lin_taps(H, AVD_T, t.ly, true);
+        double sx = (double)W / AVD_D, sy = (double)H / AVD_D;
+        t.isx = (int)sx; t.isy = (int)sy;
+        t.area_int = fabs(sx - t.isx) < 2.220446049250313e-16 && fabs(sy - t.isy) < 2.220446049250313e-16;
+        t.inv_area = 1.f / (float)(t.isx * t.isy);
+        t.thumb_2x2 = (W == 2 * AVD_T && H == 2 * AVD_T);
+        // band b of the fused kernel owns source rows [ceil(b*H/32), ceil((b+1)*H/32))
+        for (int b = 0; b <= AVD_D; b++) t.row_owner_begin[b] = b == AVD_D ? H : (int)ceil(b * sy);
+        // thumbnail row ty belongs to the band that owns its top tap row
+        int ty = 0;
+        for (int b = 0; b < AVD_D; b++) {
+            t.thumb_row_begin[b] = ty;
+            while (ty < AVD_T && (t.thumb_2x2 ? 2 * ty : t.ly[ty].i0) < t.row_owner_begin[b + 1]) ty++;
+        }
+        t.thumb_row_begin[AVD_D] = AVD_T;
+        ShapeTables *d = nullptr;
+        AVD_CUDA(ctx, cudaMalloc(&d, sizeof(ShapeTables)));
+        AVD_CUDA(ctx, cudaMemcpy(d, &t, sizeof(ShapeTables), cudaMemcpyHostToDevice));
+        ctx->tables[key] = d;
+        ctx->tables_host[key] = t;
+        it = ctx->tables.find(key);
+    }
+    *dev = it->second;
+    *host = &ctx->tables_host[key];
+    return AVD_OK;
+}
+
+int avd_ensure(avd_ctx *ctx, void **p, size_t *cap, size_t need)
+{
+    if (*cap >= need) return AVD_OK;
+    if (*p) { cudaFree(*p); *p = nullptr; *cap = 0; }
+    size_t want = need + need / 8;
+    if (cudaMalloc(p, want) != cudaSuccess) {
+        cudaGetLastError();
+        if (cudaMalloc(p, need) != cudaSuccess) {
+            cudaGetLastError();
+            ctx->err = "cudaMalloc of " + std::to_string(need) + " bytes failed";
+            return AVD_ERR_NOMEM;
+        }
+        want = need;
+    }
+    *cap = want;
+    return AVD_OK;
+}
+
+void avd_prof_begin(avd_ctx *ctx, const char *name, cudaStream_t st)
+{
+    avd_ctx::ProfRec r{name, nullptr, nullptr};
+    for (cudaEvent_t *e : {&r.a, &r.b}) {
+        if (!ctx->prof_pool.empty()) { *e = ctx->prof_pool.back(); ctx->prof_pool.pop_back(); }
+        else cudaEventCreate(e);
+    }
+    cudaEventRecord(r.a, st);
+    ctx->prof.push_back(r);
+}
+
+void avd_prof_end(avd_ctx *ctx, cudaStream_t st) { cudaEventRecord(ctx->prof.back().b, st); }
+
+// ---- C ABI -------------------------------------------------------------------------------------------
+extern "C" {
+#pragma GCC visibility push(default)
+
+const char *avd_version(void) { return "avd-b200 0.1.0 (sm_100a)"; }
+
+int avd_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+int avd_create(int device, avd_ctx **out)
+{
+    if (!out) return AVD_ERR_ARG;
+    *out = nullptr;
+    int n = avd_device_count();
+    if (n <= 0 || device < 0 || device >= n) return AVD_ERR_NODEVICE;
+    avd_ctx *ctx = new (std::nothrow) avd_ctx();
+    if (!ctx) return AVD_ERR_NOMEM;
+    ctx->device = device;
+    cudaDeviceProp prop;
+    if (cudaSetDevice(device) != cudaSuccess || cudaGetDeviceProperties(&prop, device) != cudaSuccess) {
+        cudaGetLastError(); delete ctx; return AVD_ERR_NODEVICE;
+    }
+    if (prop.major < 10) { delete ctx; return AVD_ERR_NODEVICE; }   // sm_100a SASS only: fail loudly elsewhere
+    ctx->sm_count = prop.multiProcessorCount;
+    if (cudaStreamCreateWithFlags(&ctx->compute, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&ctx->copy, cudaStreamNonBlocking) != cudaSuccess) {
+        cudaGetLastError(); delete ctx; return AVD_ERR_CUDA;
+    }
+    for (int i = 0; i < 4; i++) {
+        cudaEventCreateWithFlags(&ctx->ev_copied[i], cudaEventDisableTiming);
+        cudaEventCreateWithFlags(&ctx->ev_free[i], cudaEventDisableTiming);
+    }
+    *out = ctx;
+    return AVD_OK;
+}
+
+void avd_destroy(avd_ctx *ctx)
+{
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaDeviceSynchronize();
+    for (auto &kv : ctx->tables) cudaFree(kv.second);
+    cudaFree(ctx->gray); cudaFree(ctx->area_rows); cudaFree(ctx->k2_ws); cudaFree(ctx->ring);
+    cudaFree(ctx->thumbs); cudaFree(ctx->recs); cudaFree(ctx->area32);
+    for (int i = 0; i < 4; i++) { cudaEventDestroy(ctx->ev_copied[i]); cudaEventDestroy(ctx->ev_free[i]); }
+    cudaStreamDestroy(ctx->compute); cudaStreamDestroy(ctx->copy);
+    cudaGetLastError();
+    delete ctx;
+}
+
+const char *avd_last_error(const avd_ctx *ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+int avd_sync(avd_ctx *ctx)
+{
+    if (!ctx) return AVD_ERR_ARG;
+    AVD_CUDA(ctx, cudaSetDevice(ctx->device));
+    AVD_CUDA(ctx, cudaDeviceSynchronize());
+    return AVD_OK;
+}
+
+void *avd_host_alloc(avd_ctx *ctx, size_t bytes)
+{
+    void *p = nullptr;
+    if (!ctx || cudaSetDevice(ctx->device) != cudaSuccess) return nullptr;
+    if (cudaHostAlloc(&p, bytes, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); ctx->err = "cudaHostAlloc failed"; return nullptr; }
+    return p;
+}
+
+void avd_host_free(avd_ctx *ctx, void *p)
+{
+    (void)ctx;
+    if (p) cudaFreeHost(p);
+}
+
+uint64_t avd_launch_count(const avd_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+int avd_profile_enable(avd_ctx *ctx, int on)
+{
+    if (!ctx) return AVD_ERR_ARG;
+    ctx->profiling = on != 0;
+    return AVD_OK;
+}
+
+// JSON: {"<kernel>": {"ms": <sum of launch durations>, "launches": <n>}, ...}; clears the log.
+int avd_profile_read(avd_ctx *ctx, char *buf, size_t cap)
+{
+    if (!ctx || !buf || cap < 3) return AVD_ERR_ARG;
+    AVD_CUDA(ctx, cudaSetDevice(ctx->device));
+    AVD_CUDA(ctx, cudaDeviceSynchronize());
+    std::map<std::string, std::pair<double, long>> acc;
+    for (auto &r : ctx->prof) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, r.a, r.b) == cudaSuccess) { acc[r.name].first += ms; acc[r.name].second++; }
+        else cudaGetLastError();
+        ctx->prof_pool.push_back(r.a); ctx->prof_pool.push_back(r.b);
+    }
+    ctx->prof.clear();
+    std::string js = "{";
+    for (auto &kv : acc) {
+        char tmp[160];
+        snprintf(tmp, sizeof tmp, "%s\"%s\": {\"ms\": %.6f, \"launches\": %ld}", js.size() > 1 ? ", " : "", kv.first.c_str(), kv.second.first, kv.second.second);
+        js += tmp;
+    }
+    js += "}";
+    if (js.size() + 1 > cap) { ctx->err = "profile buffer too small"; return AVD_ERR_ARG; }
+    memcpy(buf, js.c_str(), js.size() + 1);
+    return AVD_OK;
+}
+
+int avd_set_k1_mode(avd_ctx *ctx, int mode)
+{
+    if (!ctx || mode < 0 || mode > 1) return AVD_ERR_ARG;
+    ctx->k1_mode = mode;
+    return AVD_OK;
+}
+
+static int check_shape(avd_ctx *ctx, int n, int H, int W, size_t pitch)
+{
+    if (n < 0 || H < AVD_D || W < AVD_D || pitch < (size_t)W * 3) {
+        ctx->err = "bad shape: need n >= 0, H >= 32, W >= 32, row_pitch >= 3*W";
+        return AVD_ERR_ARG;
+    }
+    return AVD_OK;
+}
+
+int avd_frames_features(avd_ctx *ctx, const uint8_t *d_bgr, int n, int H, int W, size_t row_pitch,
+                        size_t frame_stride, const uint32_t *d_prev_hash, avd_sample_rec *d_rec,
+                        uint8_t *d_thumbs, uint8_t *d_area32, void *stream)
+{
+    if (!ctx) return AVD_ERR_ARG;
+    int rc = check_shape(ctx, n, H, W, row_pitch);
+    if (rc) return rc;
+    if (n == 0) return AVD_OK;
+    if (!d_bgr || !d_rec || !d_thumbs || frame_stride < row_pitch * (size_t)H) { ctx->err = "null buffer or frame_stride < H*row_pitch"; return AVD_ERR_ARG; }
+    AVD_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = stream ? (cudaStream_t)stream : ctx->compute;
+    const ShapeTables *tab, *htab;
+    if ((rc = avd_get_tables(ctx, H, W, &tab, &htab))) return rc;
+    if (!d_area32) {
+        if ((rc = avd_ensure(ctx, (void **)&ctx->area32, &ctx->area32_cap, (size_t)n * 1024))) return rc;
+        d_area32 = ctx->area32;
+    }
+    if ((rc = k1_rec_init(ctx, d_rec, n, st))) return rc;
+    if (ctx->k1_mode == 0 && k1_fused_supported(H, W, row_pitch, frame_stride, d_bgr))
+        rc = k1_fused(ctx, d_bgr, n, H, W, row_pitch, frame_stride, tab, htab, d_rec, d_thumbs, d_area32, st);
+    else
+        rc = k1_generic(ctx, d_bgr, n, H, W, row_pitch, frame_stride, tab, htab, d_rec, d_thumbs, d_area32, st);
+    if (rc) return rc;
+    return k1_hash_finalize(ctx, d_area32, n, d_prev_hash, d_rec, st);
+}
+
+int avd_flow_stats(avd_ctx *ctx, const uint8_t *d_thumbs, int n, const uint8_t *d_prev_thumb,
+                   avd_sample_rec *d_rec, void *stream)
+{
+    if (!ctx || n < 0) return AVD_ERR_ARG;
+    if (n == 0) return AVD_OK;
+    if (!d_thumbs || !d_rec) { ctx->err = "null buffer"; return AVD_ERR_ARG; }
+    AVD_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = stream ? (cudaStream_t)stream : ctx->compute;
+    int n_pairs = d_prev_thumb ? n : n - 1;
+    return k2_flow(ctx, d_prev_thumb, d_thumbs, 0, (size_t)AVD_T * AVD_T, n_pairs, true,
+                   d_prev_thumb ? d_rec : d_rec + 1, nullptr, st);
+}
+
+int avd_flow_fields(avd_ctx *ctx, const uint8_t *d_prev, const uint8_t *d_next, int n_pairs, float *d_flow, void *stream)
+{
+    if (!ctx || n_pairs < 0) return AVD_ERR_ARG;
+    if (n_pairs == 0) return AVD_OK;
+    if (!d_prev || !d_next || !d_flow) { ctx->err = "null buffer"; return AVD_ERR_ARG; }
+    AVD_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = stream ? (cudaStream_t)stream : ctx->compute;
+    return k2_flow(ctx, d_prev, d_next, (size_t)AVD_T * AVD_T, (size_t)AVD_T * AVD_T, n_pairs, false, nullptr, d_flow, st);
+}
+
+int avd_gray(avd_ctx *ctx, const uint8_t *d_bgr, int H, int W, size_t row_pitch, uint8_t *d_gray, void *stream)
+{
+    if (!ctx) return AVD_ERR_ARG;
+    int rc = check_shape(ctx, 1, H, W, row_pitch);
+    if (rc) return rc;
+    if (!d_bgr || !d_gray) { ctx->err = "null buffer"; return AVD_ERR_ARG; }
+    AVD_CUDA(ctx, cudaSetDevice(ctx->device));
+    return k1_gray_only(ctx, d_bgr, H, W, row_pitch, d_gray, stream ? (cudaStream_t)stream : ctx->compute);
+}
+
+// Host streaming pipeline.  Frames go to a ring of device slots on the copy stream; K1 consumes a slot on
+// the compute stream as soon as its copy lands; K2 runs per chunk on the thumbnails produced so far, so
+// PCIe transfer, the per-frame kernel and the flow kernels overlap.
+int avd_analyze_host(avd_ctx *ctx, const uint8_t *const *h_frames, int n, int H, int W, size_t row_pitch,
+                     avd_sample_rec *h_rec)
+{
+    if (!ctx) return AVD_ERR_ARG;
+    int rc = check_shape(ctx, n, H, W, row_pitch);
+    if (rc) return rc;
+    if (n == 0) return AVD_OK;
+    if (!h_frames || !h_rec) { ctx->err = "null buffer"; return AVD_ERR_ARG; }
+    AVD_CUDA(ctx, cudaSetDevice(ctx->device));
+    // device frame layout inside a slot: dense rows padded to 16 bytes so the fused kernel applies
+    size_t dpitch = ((size_t)W * 3 + 15) & ~(size_t)15;
+    size_t fbytes = dpitch * H;
+    const int SLOTS = 3;
+    int per_slot = (int)((48u << 20) / fbytes);
+    if (per_slot < 1) per_slot = 1;
+    if (per_slot > 16) per_slot = 16;
+    if (per_slot > n) per_slot = n;
+    if ((rc = avd_ensure(ctx, (void **)&ctx->ring, &ctx->ring_cap, (size_t)SLOTS * per_slot * fbytes))) return rc;
+    if ((rc = avd_ensure(ctx, (void **)&ctx->thumbs, &ctx->thumbs_cap, (size_t)n * AVD_T * AVD_T))) return rc;
+    if ((rc = avd_ensure(ctx, (void **)&ctx->recs, &ctx->recs_cap, (size_t)n * sizeof(avd_sample_rec)))) return rc;
+    if ((rc = avd_ensure(ctx, (void **)&ctx->area32, &ctx->area32_cap, (size_t)n * 1024))) return rc;
+    const ShapeTables *tab, *htab;
+    if ((rc = avd_get_tables(ctx, H, W, &tab, &htab))) return rc;
+    int chunk = 0;
+    for (int f0 = 0; f0 < n; f0 += per_slot, chunk++) {
+        int nb = n - f0 < per_slot ? n - f0 : per_slot;
+        int slot = chunk % SLOTS;
+        uint8_t *dst = ctx->ring + (size_t)slot * per_slot * fbytes;
+        if (chunk >= SLOTS) AVD_CUDA(ctx, cudaStreamWaitEvent(ctx->copy, ctx->ev_free[slot], 0));
+        for (int j = 0; j < nb; j++) {
+            if (!h_frames[f0 + j]) { ctx->err = "null frame pointer"; cudaStreamSynchronize(ctx->copy); cudaStreamSynchronize(ctx->compute); return AVD_ERR_ARG; }
+            if (dpitch == row_pitch)
+                AVD_CUDA(ctx, cudaMemcpyAsync(dst + (size_t)j * fbytes, h_frames[f0 + j], fbytes, cudaMemcpyHostToDevice, ctx->copy));
+            else
+                AVD_CUDA(ctx, cudaMemcpy2DAsync(dst + (size_t)j * fbytes, dpitch, h_frames[f0 + j], row_pitch, (size_t)W * 3, H,
+                                               cudaMemcpyHostToDevice, ctx->copy));
+        }
+        AVD_CUDA(ctx, cudaEventRecord(ctx->ev_copied[slot], ctx->copy));
+        AVD_CUDA(ctx, cudaStreamWaitEvent(ctx->compute, ctx->ev_copied[slot], 0));
+        avd_sample_rec *rec = ctx->recs + f0;
+        uint8_t *th = ctx->thumbs + (size_t)f0 * AVD_T * AVD_T;
+        const uint32_t *prev_hash = f0 > 0 ? ctx->recs[f0 - 1].hash : nullptr;
+        if ((rc = avd_frames_features(ctx, dst, nb, H, W, dpitch, fbytes, prev_hash, rec, th, ctx->area32 + (size_t)f0 * 1024, ctx->compute))) return rc;
+        AVD_CUDA(ctx, cudaEventRecord(ctx->ev_free[slot], ctx->compute));
+        if ((rc = avd_flow_stats(ctx, th, nb, f0 > 0 ? th - (size_t)AVD_T * AVD_T : nullptr, rec, ctx->compute))) return rc;
+    }
+    AVD_CUDA(ctx, cudaMemcpyAsync(h_rec, ctx->recs, (size_t)n * sizeof(avd_sample_rec), cudaMemcpyDeviceToHost, ctx->compute));
+    AVD_CUDA(ctx, cudaStreamSynchronize(ctx->compute));
+    return AVD_OK;
+}
+
+#pragma GCC visibility pop
+}  // extern "C"

@@ -1,0 +1,118 @@
+// Internal declarations shared by the translation units of libavd.so (not part of the C ABI).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string>
+#include <map>
+#include <utility>
+#include <vector>
+#include "../../include/avd.h"
+
+#define AVD_D 32            // aHash side
+#define AVD_T 320           // thumbnail side
+#define AVD_LEVELS 4        // Farneback pyramid: 40, 80, 160, 320
+
+// One INTER_AREA destination cell along one axis (OpenCV computeResizeAreaTab, restated):
+// taps in order: optional head (index s1-1, weight ah), s in [s1,s2) weight am, optional tail (index s2, weight at).
+struct AreaCell {
+    int s1, s2;
+    float ah, am, at;
+    int has_head, has_tail;
+};
+
+// INTER_LINEAR (8-bit, 11-bit fixed point) tap of one destination index along one axis.
+struct LinTap {
+    int i0, i1;      // source indices (already clamped / clipped)
+    int a0, a1;      // weights, sum 2048
+};
+
+// Per-(H,W) resampling tables, resident in device memory.
+struct ShapeTables {
+    AreaCell ax[AVD_D], ay[AVD_D];
+    LinTap lx[AVD_T], ly[AVD_T];
+    int area_int;            // 1: both scales integer -> block-sum path
+    int isx, isy;            // integer scales (area_int)
+    float inv_area;          // float(1/(isx*isy))
+    int thumb_2x2;           // source is exactly 640x640 -> 2x2 mean
+    int row_owner_begin[AVD_D + 1];  // first source row owned by band b (fused kernel); [32] = H
+    int thumb_row_begin[AVD_D + 1];  // first thumbnail row whose top tap lies in band b; [32] = 320
+};
+
+struct avd_ctx {
+    int device = 0;
+    int sm_count = 0;
+    cudaStream_t compute = nullptr, copy = nullptr;
+    std::string err;
+    uint64_t launches = 0;
+    int k1_mode = 0;
+    std::map<std::pair<int, int>, ShapeTables *> tables;   // device pointers
+    std::map<std::pair<int, int>, ShapeTables> tables_host;
+    // generic K1 scratch
+    uint8_t *gray = nullptr; size_t gray_cap = 0;
+    float *area_rows = nullptr; size_t area_rows_cap = 0;
+    // K2 workspace (see k2_flow.cu)
+    void *k2_ws = nullptr; size_t k2_ws_cap = 0; int k2_batch = 0;
+    // host streaming ring (avd_analyze_host)
+    uint8_t *ring = nullptr; size_t ring_cap = 0;
+    cudaEvent_t ev_copied[4] = {}, ev_free[4] = {};
+    uint8_t *thumbs = nullptr; size_t thumbs_cap = 0;
+    avd_sample_rec *recs = nullptr; size_t recs_cap = 0;
+    uint8_t *area32 = nullptr; size_t area32_cap = 0;
+    // optional per-kernel timing (avd_profile_enable): CUDA events around every launch, on its stream
+    bool profiling = false;
+    struct ProfRec { const char *name; cudaEvent_t a, b; };
+    std::vector<ProfRec> prof;
+    std::vector<cudaEvent_t> prof_pool;
+};
+
+#define AVD_CUDA(ctx, call)                                                                   \
+    do {                                                                                      \
+        cudaError_t e__ = (call);                                                             \
+        if (e__ != cudaSuccess) {                                                             \
+            (ctx)->err = std::string(#call) + ": " + cudaGetErrorString(e__);                 \
+            cudaGetLastError();                                                               \
+            return AVD_ERR_CUDA;                                                              \
+        }                                                                                     \
+    } while (0)
+
+#define AVD_LAUNCH_CHECK(ctx, name)                                                           \
+    do {                                                                                      \
+        (ctx)->launches++;                                                                    \
+        cudaError_t e__ = cudaGetLastError();                                                 \
+        if (e__ != cudaSuccess) {                                                             \
+            (ctx)->err = std::string("launch ") + name + ": " + cudaGetErrorString(e__);      \
+            return AVD_ERR_CUDA;                                                              \
+        }                                                                                     \
+    } while (0)
+
+void avd_prof_begin(avd_ctx *ctx, const char *name, cudaStream_t st);
+void avd_prof_end(avd_ctx *ctx, cudaStream_t st);
+
+// AVD_LAUNCH(ctx, "name", stream, kernel<<<grid, block, smem, stream>>>(args...));
+#define AVD_LAUNCH(ctx, name, st, ...)                                                        \
+    do {                                                                                      \
+        if ((ctx)->profiling) avd_prof_begin(ctx, name, st);                                  \
+        __VA_ARGS__;                                                                          \
+        if ((ctx)->profiling) avd_prof_end(ctx, st);                                          \
+        AVD_LAUNCH_CHECK(ctx, name);                                                          \
+    } while (0)
+
+int avd_ensure(avd_ctx *ctx, void **p, size_t *cap, size_t need);   // grow-only device buffer
+int avd_get_tables(avd_ctx *ctx, int H, int W, const ShapeTables **dev, const ShapeTables **host);
+
+// k1_generic.cu
+int k1_rec_init(avd_ctx *ctx, avd_sample_rec *d_rec, int n, cudaStream_t st);
+int k1_generic(avd_ctx *ctx, const uint8_t *d_bgr, int n, int H, int W, size_t pitch, size_t fstride,
+               const ShapeTables *tab, const ShapeTables *htab, avd_sample_rec *d_rec, uint8_t *d_thumbs,
+               uint8_t *d_area32, cudaStream_t st);
+int k1_gray_only(avd_ctx *ctx, const uint8_t *d_bgr, int H, int W, size_t pitch, uint8_t *d_gray, cudaStream_t st);
+int k1_hash_finalize(avd_ctx *ctx, const uint8_t *d_area32, int n, const uint32_t *d_prev_hash,
+                     avd_sample_rec *d_rec, cudaStream_t st);
+// k1_fused.cu
+bool k1_fused_supported(int H, int W, size_t pitch, size_t fstride, const void *base);
+int k1_fused(avd_ctx *ctx, const uint8_t *d_bgr, int n, int H, int W, size_t pitch, size_t fstride,
+             const ShapeTables *tab, const ShapeTables *htab, avd_sample_rec *d_rec, uint8_t *d_thumbs,
+             uint8_t *d_area32, cudaStream_t st);
+// k2_flow.cu
+int k2_flow(avd_ctx *ctx, const uint8_t *d_prev, const uint8_t *d_next, size_t prev_stride, size_t next_stride,
+            int n_pairs, bool shared_chain, avd_sample_rec *d_rec_first, float *d_flow_out, cudaStream_t st);

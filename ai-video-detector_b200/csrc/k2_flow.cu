@@ -1,0 +1,451 @@
+// K2: batched dense Farneback optical flow on 320x320 thumbnails and its magnitude statistics.
+//
+// Replaces cv2.calcOpticalFlowFarneback(prev, small, None, 0.5, 3, 15, 3, 5, 1.2, 0) (video.py:45) and
+// np.mean/np.var of the magnitude (video.py:46-48).  Algorithm restated in SURVEY.md A.5:
+// 4 pyramid levels (40,80,160,320), polynomial expansion n=5 sigma=1.2, 15x15 box window, 3 iterations.
+//
+// B200 design: the batch dimension is the image / pair index.  The per-IMAGE work (pyramid + polynomial
+// expansion) is done once per thumbnail, not once per pair as the CPU library does (each thumbnail is
+// "next" of one pair and "prev" of the following one).  All intermediates are planar float32 so every
+// warp access is a contiguous 128-byte line; they are sized to stay L2-resident per batch.
+// Compiled with -fmad=false: the float sequences round exactly like the scalar library code.
+#include "avd_internal.h"
+#include <math.h>
+
+namespace {
+
+constexpr int T = AVD_T;
+constexpr int PYR_PX = 40 * 40 + 80 * 80 + 160 * 160 + 320 * 320;   // 136000 pixels over the 4 levels
+__host__ __device__ constexpr int lvl_size(int k) { return T >> k; }
+__host__ __device__ constexpr int lvl_off(int k) { return k == 3 ? 0 : k == 2 ? 1600 : k == 1 ? 8000 : 33600; }
+
+struct ImgSrc {           // where image i of the batch lives
+    const uint8_t *a, *b; // chain: a = thumbs, b = optional predecessor.  pairs: a = prev[], b = next[]
+    size_t sa, sb;        // strides in bytes
+    int mode;             // 0 chain without predecessor, 1 chain with predecessor, 2 explicit pairs
+};
+__device__ __forceinline__ const uint8_t *img_ptr(const ImgSrc &s, int i)
+{
+    if (s.mode == 0) return s.a + (size_t)i * s.sa;
+    if (s.mode == 1) return i == 0 ? s.b : s.a + (size_t)(i - 1) * s.sa;
+    return (i & 1) ? s.b + (size_t)(i >> 1) * s.sb : s.a + (size_t)(i >> 1) * s.sa;
+}
+
+struct FlowConst {
+    float g[6], xg[6], xxg[6];          // polynomial-expansion Gaussian moments, index |k|
+    double ig11, ig03, ig33, ig55;
+    float k1[2], k2[5], k3[10];         // pyramid blur kernels: centre..edge for levels 1,2,3 (level 0 is .5/.25)
+};
+__constant__ FlowConst FC;
+
+__device__ __forceinline__ int r101(int i, int n) { return i < 0 ? -i : (i >= n ? 2 * n - 2 - i : i); }
+__device__ __forceinline__ int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
+
+// ---- pyramid -----------------------------------------------------------------------------------------
+// GaussianBlur(ksize, sigma) of the full-resolution image (row pass then column pass, symmetric pairs
+// summed first) evaluated only at the taps the following INTER_LINEAR / 2x2-area resize reads.
+template <int R>
+__device__ __forceinline__ float blur_row(const uint8_t *__restrict__ row, int x, const float *__restrict__ k)
+{
+    float a = k[0] * (float)row[x];
+#pragma unroll
+    for (int j = 1; j <= R; j++) a = a + k[j] * ((float)row[r101(x - j, T)] + (float)row[r101(x + j, T)]);
+    return a;
+}
+
+template <int R, int NX, int NY>
+__device__ __forceinline__ void blur_taps(const uint8_t *__restrict__ img, int xc, int yc, const float *__restrict__ k, float out[NY][NX])
+{
+    // rows yc-R .. yc+NY-1+R, columns xc .. xc+NX-1
+    float t[NY + 2 * R][NX];
+#pragma unroll
+    for (int r = 0; r < NY + 2 * R; r++) {
+        const uint8_t *row = img + (size_t)r101(yc - R + r, T) * T;
+#pragma unroll
+        for (int c = 0; c < NX; c++) t[r][c] = blur_row<R>(row, xc + c, k);
+    }
+#pragma unroll
+    for (int oy = 0; oy < NY; oy++)
+#pragma unroll
+        for (int c = 0; c < NX; c++) {
+            float a = k[0] * t[oy + R][c];
+#pragma unroll
+            for (int j = 1; j <= R; j++) a = a + k[j] * (t[oy + R - j][c] + t[oy + R + j][c]);
+            out[oy][c] = a;
+        }
+}
+
+__global__ void __launch_bounds__(128) pyr_kernel(ImgSrc src, float *__restrict__ pyr)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= PYR_PX) return;
+    int img_i = blockIdx.y;
+    const uint8_t *img = img_ptr(src, img_i);
+    float *out = pyr + (size_t)img_i * PYR_PX;
+    const float k0[2] = {0.5f, 0.25f};
+    if (i >= lvl_off(0)) {
+        int p = i - lvl_off(0), y = p / 320, x = p % 320;
+        float o[1][1];
+        blur_taps<1, 1, 1>(img, x, y, k0, o);
+        out[i] = o[0][0];
+    } else if (i >= lvl_off(1)) {          // 320 -> 160: exact 2x => 2x2 area mean
+        int p = i - lvl_off(1), y = p / 160, x = p % 160;
+        float o[2][2];
+        blur_taps<1, 2, 2>(img, 2 * x, 2 * y, FC.k1, o);
+        out[i] = (((o[0][0] + o[0][1]) + o[1][0]) + o[1][1]) * 0.25f;
+    } else if (i >= lvl_off(2)) {          // 320 -> 80: bilinear at 4x+1.5 (weights .5/.5)
+        int p = i - lvl_off(2), y = p / 80, x = p % 80;
+        float o[2][2];
+        blur_taps<4, 2, 2>(img, 4 * x + 1, 4 * y + 1, FC.k2, o);
+        float r0 = o[0][0] * 0.5f + o[0][1] * 0.5f, r1 = o[1][0] * 0.5f + o[1][1] * 0.5f;
+        out[i] = r0 * 0.5f + r1 * 0.5f;
+    } else {                               // 320 -> 40: bilinear at 8x+3.5
+        int y = i / 40, x = i % 40;
+        float o[2][2];
+        blur_taps<9, 2, 2>(img, 8 * x + 3, 8 * y + 3, FC.k3, o);
+        float r0 = o[0][0] * 0.5f + o[0][1] * 0.5f, r1 = o[1][0] * 0.5f + o[1][1] * 0.5f;
+        out[i] = r0 * 0.5f + r1 * 0.5f;
+    }
+}
+
+// ---- polynomial expansion ----------------------------------------------------------------------------
+// R[img][c][y][x], c = 0..4, planar.  Vertical pass float32 -> shared, horizontal pass float64 accumulators.
+constexpr int PE_TW = 32, PE_TH = 8, PE_HALO = 5;
+
+__global__ void __launch_bounds__(PE_TW *PE_TH) polyexp_kernel(const float *__restrict__ pyr, float *__restrict__ Rall, int k)
+{
+    const int s = lvl_size(k);
+    const float *I = pyr + (size_t)blockIdx.z * PYR_PX + lvl_off(k);
+    float *R = Rall + (size_t)blockIdx.z * PYR_PX * 5 + (size_t)lvl_off(k) * 5;
+    __shared__ float v[3][PE_TH][PE_TW + 2 * PE_HALO];
+    int x0 = blockIdx.x * PE_TW, y0 = blockIdx.y * PE_TH;
+    int tid = threadIdx.y * PE_TW + threadIdx.x;
+    for (int idx = tid; idx < PE_TH * (PE_TW + 2 * PE_HALO); idx += PE_TW * PE_TH) {
+        int ty = idx / (PE_TW + 2 * PE_HALO), tc = idx % (PE_TW + 2 * PE_HALO);
+        int gx = clampi(x0 + tc - PE_HALO, 0, s - 1), gy = min(y0 + ty, s - 1);
+        float c0 = I[(size_t)gy * s + gx];
+        float r0 = c0 * FC.g[0], r1 = 0.f, r2 = 0.f;
+#pragma unroll
+        for (int j = 1; j <= 5; j++) {
+            float a = I[(size_t)max(gy - j, 0) * s + gx], b = I[(size_t)min(gy + j, s - 1) * s + gx];
+            float p = a + b;
+            r0 = r0 + FC.g[j] * p;
+            r1 = r1 + FC.xg[j] * (b - a);
+            r2 = r2 + FC.xxg[j] * p;
+        }
+        v[0][ty][tc] = r0; v[1][ty][tc] = r1; v[2][ty][tc] = r2;
+    }
+    __syncthreads();
+    int x = x0 + threadIdx.x, y = y0 + threadIdx.y;
+    if (x >= s || y >= s) return;
+    const int c = threadIdx.x + PE_HALO, ty = threadIdx.y;
+    double b1 = (double)(v[0][ty][c] * FC.g[0]), b2 = 0, b3 = (double)(v[1][ty][c] * FC.g[0]), b4 = 0,
+           b5 = (double)(v[2][ty][c] * FC.g[0]), b6 = 0;
+#pragma unroll
+    for (int j = 1; j <= 5; j++) {
+        float p0 = v[0][ty][c + j], m0 = v[0][ty][c - j], p1 = v[1][ty][c + j], m1 = v[1][ty][c - j],
+              p2 = v[2][ty][c + j], m2 = v[2][ty][c - j];
+        double tg = (double)(p0 + m0);
+        b1 += tg * (double)FC.g[j];
+        b4 += tg * (double)FC.xxg[j];
+        b2 += (double)((p0 - m0) * FC.xg[j]);
+        b3 += (double)((p1 + m1) * FC.g[j]);
+        b6 += (double)((p1 - m1) * FC.xg[j]);
+        b5 += (double)((p2 + m2) * FC.g[j]);
+    }
+    size_t plane = (size_t)s * s, o = (size_t)y * s + x;
+    R[o] = (float)(b3 * FC.ig11);
+    R[plane + o] = (float)(b2 * FC.ig11);
+    R[2 * plane + o] = (float)(b1 * FC.ig03 + b5 * FC.ig33);
+    R[3 * plane + o] = (float)(b1 * FC.ig03 + b4 * FC.ig33);
+    R[4 * plane + o] = (float)(b6 * FC.ig55);
+}
+
+// ---- update matrices ---------------------------------------------------------------------------------
+// FLOWSRC: 0 = zero flow (coarsest level), 1 = flow of this level, 2 = 2x bilinear upsample of the
+// coarser level's flow times 2 (the library's resize(prevFlow)*1/pyr_scale, fused here).
+__device__ __forceinline__ float up2_axis_w(int d, int ssz, int &i0, int &i1, bool clamp_w)
+{
+    // INTER_LINEAR 2x upsampling tap of destination index d: f = d/2 - .25
+    float f = (float)((d + 0.5) * 0.5 - 0.5);
+    int s = (int)floorf(f);
+    f -= (float)s;
+    if (clamp_w) {                       // x axis: weight clamped at the ends
+        if (s < 0) { f = 0.f; s = 0; }
+        if (s >= ssz - 1) { f = 0.f; s = ssz - 1; }
+        i0 = s; i1 = min(s + 1, ssz - 1);
+    } else {                             // y axis: rows clipped, weight kept
+        i0 = clampi(s, 0, ssz - 1); i1 = clampi(s + 1, 0, ssz - 1);
+    }
+    return f;
+}
+
+__device__ __forceinline__ float up2_sample(const float *__restrict__ c, int cs, int x, int y)
+{
+    int x0, x1, y0, y1;
+    float fx = up2_axis_w(x, cs, x0, x1, true), fy = up2_axis_w(y, cs, y0, y1, false);
+    float ax0 = 1.f - fx, ay0 = 1.f - fy;
+    bool edge = (x0 == cs - 1);          // library: beyond xmax the row pass is S[sx]*1
+    float r0 = edge ? c[(size_t)y0 * cs + x0] * 1.f : c[(size_t)y0 * cs + x0] * ax0 + c[(size_t)y0 * cs + x1] * fx;
+    float r1 = edge ? c[(size_t)y1 * cs + x0] * 1.f : c[(size_t)y1 * cs + x0] * ax0 + c[(size_t)y1 * cs + x1] * fx;
+    return (r0 * ay0 + r1 * fy) * 2.f;
+}
+
+template <int FLOWSRC>
+__global__ void __launch_bounds__(256) update_matrices_kernel(const float *__restrict__ Rall, const float *__restrict__ flow,
+                                                              const float *__restrict__ coarse, float *__restrict__ Mall,
+                                                              float *__restrict__ flow_store, int k, int pair_img_mode)
+{
+    const int s = lvl_size(k);
+    int x = blockIdx.x * 32 + threadIdx.x, y = blockIdx.y * 8 + threadIdx.y, p = blockIdx.z;
+    if (x >= s || y >= s) return;
+    int ia = pair_img_mode == 2 ? 2 * p : p, ib = ia + 1;
+    size_t plane = (size_t)s * s, o = (size_t)y * s + x;
+    const float *R0 = Rall + (size_t)ia * PYR_PX * 5 + (size_t)lvl_off(k) * 5;
+    const float *R1 = Rall + (size_t)ib * PYR_PX * 5 + (size_t)lvl_off(k) * 5;
+    float dx = 0.f, dy = 0.f;
+    if (FLOWSRC == 1) {
+        dx = flow[(size_t)p * 2 * plane + o]; dy = flow[(size_t)p * 2 * plane + plane + o];
+    } else if (FLOWSRC == 2) {
+        int cs = s >> 1;
+        const float *cf = coarse + (size_t)p * 2 * cs * cs;
+        dx = up2_sample(cf, cs, x, y); dy = up2_sample(cf + (size_t)cs * cs, cs, x, y);
+    }
+    float fx = (float)x + dx, fy = (float)y + dy;
+    int x1 = (int)floorf(fx), y1 = (int)floorf(fy);
+    fx -= (float)x1; fy -= (float)y1;
+    float r2, r3, r4, r5, r6;
+    float q0 = R0[o], q1 = R0[plane + o], q2 = R0[2 * plane + o], q3 = R0[3 * plane + o], q4 = R0[4 * plane + o];
+    if ((unsigned)x1 < (unsigned)(s - 1) && (unsigned)y1 < (unsigned)(s - 1)) {
+        float a00 = (1.f - fx) * (1.f - fy), a01 = fx * (1.f - fy), a10 = (1.f - fx) * fy, a11 = fx * fy;
+        size_t b = (size_t)y1 * s + x1;
+#define BIL(c) (((a00 * R1[(c) * plane + b] + a01 * R1[(c) * plane + b + 1]) + a10 * R1[(c) * plane + b + s]) + a11 * R1[(c) * plane + b + s + 1])
+        r2 = BIL(0); r3 = BIL(1); r4 = BIL(2); r5 = BIL(3); r6 = BIL(4);
+#undef BIL
+        r4 = (q2 + r4) * 0.5f; r5 = (q3 + r5) * 0.5f; r6 = (q4 + r6) * 0.25f;
+    } else {
+        r2 = r3 = 0.f; r4 = q2; r5 = q3; r6 = q4 * 0.5f;
+    }
+    r2 = (q0 - r2) * 0.5f;
+    r3 = (q1 - r3) * 0.5f;
+    r2 = r2 + (r4 * dy + r6 * dx);
+    r3 = r3 + (r6 * dy + r5 * dx);
+    const int B = 5;
+    if ((unsigned)(x - B) >= (unsigned)(s - 2 * B) || (unsigned)(y - B) >= (unsigned)(s - 2 * B)) {
+        const float border[5] = {0.14f, 0.14f, 0.4472f, 0.4472f, 0.4472f};
+        float sc = (x < B ? border[x] : 1.f) * (x >= s - B ? border[s - x - 1] : 1.f) *
+                   (y < B ? border[y] : 1.f) * (y >= s - B ? border[s - y - 1] : 1.f);
+        r2 *= sc; r3 *= sc; r4 *= sc; r5 *= sc; r6 *= sc;
+    }
+    float *M = Mall + (size_t)p * 5 * T * T;
+    M[o] = r4 * r4 + r6 * r6;
+    M[plane + o] = (r4 + r5) * r6;
+    M[2 * plane + o] = r5 * r5 + r6 * r6;
+    M[3 * plane + o] = r4 * r2 + r6 * r3;
+    M[4 * plane + o] = r6 * r2 + r5 * r3;
+    (void)flow_store;
+}
+
+// ---- 15x15 box sums (float64) + 2x2 solve -------------------------------------------------------------
+constexpr int BS_TW = 32, BS_TH = 32, BS_M = 7, BS_CW = BS_TW + 2 * BS_M;   // 46 columns incl. halo
+constexpr int BS_PITCH = BS_CW + 1;
+
+__global__ void __launch_bounds__(256) blur_solve_kernel(const float *__restrict__ Mall, float *__restrict__ flow, int k)
+{
+    const int s = lvl_size(k);
+    extern __shared__ double vs[];      // [5][BS_TH][BS_PITCH]
+    int x0 = blockIdx.x * BS_TW, y0 = blockIdx.y * BS_TH, p = blockIdx.z;
+    size_t plane = (size_t)s * s;
+    const float *M = Mall + (size_t)p * 5 * T * T;
+    int tid = threadIdx.y * 32 + threadIdx.x;
+    if (tid < 5 * BS_CW) {
+        int c = tid / BS_CW, col = tid % BS_CW;
+        int gx = clampi(x0 + col - BS_M, 0, s - 1);
+        const float *Mc = M + c * plane + gx;
+        double run = 0;
+        for (int j = -BS_M; j <= BS_M; j++) run += (double)Mc[(size_t)clampi(y0 + j, 0, s - 1) * s];
+        for (int r = 0; r < BS_TH; r++) {
+            vs[(c * BS_TH + r) * BS_PITCH + col] = run;
+            run += (double)Mc[(size_t)clampi(y0 + r + BS_M + 1, 0, s - 1) * s] - (double)Mc[(size_t)clampi(y0 + r - BS_M, 0, s - 1) * s];
+        }
+    }
+    __syncthreads();
+    int x = x0 + threadIdx.x;
+    if (x >= s) return;
+    const double scale = 1.0 / 225.0;
+    for (int ry = threadIdx.y; ry < BS_TH; ry += 8) {
+        int y = y0 + ry;
+        if (y >= s) break;
+        double a[5];
+#pragma unroll
+        for (int c = 0; c < 5; c++) {
+            const double *row = vs + (c * BS_TH + ry) * BS_PITCH + threadIdx.x;
+            double t = 0;
+#pragma unroll
+            for (int j = 0; j < 15; j++) t += row[j];
+            a[c] = t * scale;
+        }
+        double idet = 1.0 / (a[0] * a[2] - a[1] * a[1] + 1e-3);
+        size_t o = (size_t)y * s + x;
+        flow[(size_t)p * 2 * plane + o] = (float)((a[0] * a[4] - a[1] * a[3]) * idet);
+        flow[(size_t)p * 2 * plane + plane + o] = (float)((a[2] * a[3] - a[1] * a[4]) * idet);
+    }
+}
+
+// ---- magnitude statistics -----------------------------------------------------------------------------
+__device__ __forceinline__ double block_sum(double v, double *sh)
+{
+    for (int o = 16; o; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+    __syncthreads();
+    if (l == 0) sh[w] = v;
+    __syncthreads();
+    if (w == 0) {
+        v = l < (int)(blockDim.x >> 5) ? sh[l] : 0.0;
+        for (int o = 16; o; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+        if (l == 0) sh[32] = v;
+    }
+    __syncthreads();
+    return sh[32];
+}
+
+__global__ void __launch_bounds__(1024) magstats_kernel(const float *__restrict__ flow, avd_sample_rec *rec, int rec_stride_pairs)
+{
+    __shared__ double sh[33];
+    int p = blockIdx.x;
+    const float *fx = flow + (size_t)p * 2 * T * T, *fy = fx + T * T;
+    double s = 0;
+    for (int i = threadIdx.x; i < T * T; i += blockDim.x) s += (double)sqrtf(fx[i] * fx[i] + fy[i] * fy[i]);
+    float mean = (float)(block_sum(s, sh) / (double)(T * T));
+    double q = 0;
+    for (int i = threadIdx.x; i < T * T; i += blockDim.x) {
+        float d = sqrtf(fx[i] * fx[i] + fy[i] * fy[i]) - mean;
+        q += (double)(d * d);
+    }
+    float var = (float)(block_sum(q, sh) / (double)(T * T));
+    if (threadIdx.x == 0) {
+        avd_sample_rec *r = rec + (size_t)p * rec_stride_pairs;
+        r->flow_mean = mean; r->flow_var = var; r->flags |= AVD_REC_HAS_FLOW;
+    }
+}
+
+__global__ void interleave_kernel(const float *__restrict__ flow, float *__restrict__ out, int n_pairs)
+{
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    size_t total = (size_t)n_pairs * T * T;
+    if (i >= total) return;
+    size_t p = i / (T * T), o = i % (T * T);
+    out[2 * i] = flow[p * 2 * T * T + o];
+    out[2 * i + 1] = flow[p * 2 * T * T + T * T + o];
+}
+
+FlowConst make_consts()
+{
+    FlowConst c{};
+    const int n = 5; const double sigma = 1.2;
+    float g[11], *gc = g + n;
+    double sum = 0;
+    for (int x = -n; x <= n; x++) { gc[x] = (float)exp(-x * x / (2 * sigma * sigma)); sum += gc[x]; }
+    sum = 1. / sum;
+    for (int x = -n; x <= n; x++) gc[x] = (float)(gc[x] * sum);
+    for (int x = 0; x <= n; x++) { c.g[x] = gc[x]; c.xg[x] = (float)(x * gc[x]); c.xxg[x] = (float)(x * x * gc[x]); }
+    double a = 0, b = 0, cc = 0, d = 0;
+    for (int y = -n; y <= n; y++)
+        for (int x = -n; x <= n; x++) {
+            double w = (double)gc[y] * gc[x];
+            a += w; b += w * x * x; cc += w * x * x * x * x; d += w * x * x * y * y;
+        }
+    c.ig11 = 1.0 / b; c.ig55 = 1.0 / d;
+    double det = a * (cc * cc - d * d) - b * (b * cc - b * d) + b * (b * d - b * cc);
+    c.ig03 = -(b * cc - b * d) / det;
+    c.ig33 = (a * cc - b * b) / det;
+    auto gk = [](int ksize, double s, float *out) {   // centre..edge
+        double t[32], sm = 0;
+        for (int i = 0; i < ksize; i++) { double x = i - (ksize - 1) * 0.5; t[i] = exp(-x * x / (2 * s * s)); sm += t[i]; }
+        for (int i = 0; i <= ksize / 2; i++) out[i] = (float)(t[ksize / 2 + i] / sm);
+    };
+    gk(3, 0.5, c.k1); gk(9, 1.5, c.k2); gk(19, 3.5, c.k3);
+    return c;
+}
+
+}  // namespace
+
+// Workspace per batch of NI images / NP pairs (floats):
+//   pyr  NI*136000 | R  NI*136000*5 | M  NP*5*320*320 | flowA, flowB  NP*2*320*320 each
+static size_t k2_ws_bytes(int ni, int np)
+{
+    return sizeof(float) * ((size_t)ni * PYR_PX * 6 + (size_t)np * T * T * 9);
+}
+
+int k2_flow(avd_ctx *ctx, const uint8_t *d_prev, const uint8_t *d_next, size_t prev_stride, size_t next_stride,
+            int n_pairs, bool shared_chain, avd_sample_rec *d_rec_first, float *d_flow_out, cudaStream_t st)
+{
+    // shared_chain: images are one chain; pair p = (image p, image p+1); d_prev = optional predecessor
+    // thumbnail (may be NULL), d_next = thumbs.  Otherwise explicit pairs (d_prev[p], d_next[p]).
+    static bool consts_done[64] = {};
+    if (!consts_done[ctx->device & 63]) {
+        FlowConst c = make_consts();
+        AVD_CUDA(ctx, cudaMemcpyToSymbol(FC, &c, sizeof(c)));
+        consts_done[ctx->device & 63] = true;
+    }
+    if (n_pairs <= 0) return AVD_OK;
+    const int MAXP = 128;   // pairs per batch
+    int rc;
+    int cap_np = n_pairs < MAXP ? n_pairs : MAXP, cap_ni = shared_chain ? cap_np + 1 : 2 * cap_np;
+    if ((rc = avd_ensure(ctx, &ctx->k2_ws, &ctx->k2_ws_cap, k2_ws_bytes(cap_ni, cap_np)))) return rc;
+    static bool attr_done = false;
+    size_t bs_smem = sizeof(double) * 5 * BS_TH * BS_PITCH;
+    if (!attr_done) {
+        AVD_CUDA(ctx, cudaFuncSetAttribute(blur_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bs_smem));
+        attr_done = true;
+    }
+    for (int p0 = 0; p0 < n_pairs; p0 += MAXP) {
+        int np = n_pairs - p0 < MAXP ? n_pairs - p0 : MAXP;
+        int ni = shared_chain ? np + 1 : 2 * np;
+        float *pyr = (float *)ctx->k2_ws, *R = pyr + (size_t)ni * PYR_PX, *M = R + (size_t)ni * PYR_PX * 5;
+        float *flowA = M + (size_t)np * 5 * T * T, *flowB = flowA + (size_t)np * 2 * T * T;
+        ImgSrc src{};
+        int mode;
+        if (shared_chain) {
+            // chain image j of this batch = global chain image p0 + j
+            if (d_prev && p0 == 0) { src.mode = 1; src.a = d_next; src.b = d_prev; src.sa = next_stride; }
+            else { src.mode = 0; src.a = d_next + (size_t)(p0 - (d_prev ? 1 : 0)) * next_stride; src.sa = next_stride; }
+            mode = 0;
+        } else {
+            src.mode = 2; src.a = d_prev + (size_t)p0 * prev_stride; src.b = d_next + (size_t)p0 * next_stride;
+            src.sa = prev_stride; src.sb = next_stride; mode = 2;
+        }
+        AVD_LAUNCH(ctx, "pyr", st, pyr_kernel<<<dim3((PYR_PX + 127) / 128, ni), 128, 0, st>>>(src, pyr));
+        for (int k = 3; k >= 0; k--) {
+            int s = lvl_size(k);
+            AVD_LAUNCH(ctx, "polyexp", st, polyexp_kernel<<<dim3((s + PE_TW - 1) / PE_TW, (s + PE_TH - 1) / PE_TH, ni), dim3(PE_TW, PE_TH), 0, st>>>(pyr, R, k));
+        }
+        float *cur = flowA, *prev = flowB;
+        for (int k = 3; k >= 0; k--) {
+            int s = lvl_size(k);
+            dim3 gu((s + 31) / 32, (s + 7) / 8, np), bu(32, 8);
+            dim3 gb((s + BS_TW - 1) / BS_TW, (s + BS_TH - 1) / BS_TH, np);
+            if (k == 3) {
+                AVD_LAUNCH(ctx, "update_matrices", st, update_matrices_kernel<0><<<gu, bu, 0, st>>>(R, nullptr, nullptr, M, nullptr, k, mode));
+            } else {
+                AVD_LAUNCH(ctx, "update_matrices", st, update_matrices_kernel<2><<<gu, bu, 0, st>>>(R, nullptr, prev, M, nullptr, k, mode));
+            }
+            for (int it = 0; it < 3; it++) {
+                AVD_LAUNCH(ctx, "blur_solve", st, blur_solve_kernel<<<gb, bu, bs_smem, st>>>(M, cur, k));
+                if (it < 2) {
+                    AVD_LAUNCH(ctx, "update_matrices", st, update_matrices_kernel<1><<<gu, bu, 0, st>>>(R, cur, nullptr, M, nullptr, k, mode));
+                }
+            }
+            float *t = cur; cur = prev; prev = t;   // prev now holds this level's flow
+        }
+        if (d_rec_first) {
+            // chain: pair p0+j -> record of its "next" image
+            AVD_LAUNCH(ctx, "magstats", st, magstats_kernel<<<np, 1024, 0, st>>>(prev, d_rec_first + p0, 1));
+        }
+        if (d_flow_out) {
+            size_t total = (size_t)np * T * T;
+            AVD_LAUNCH(ctx, "interleave", st, interleave_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(prev, d_flow_out + (size_t)p0 * T * T * 2, np));
+        }
+    }
+    return AVD_OK;
+}

@@ -1,0 +1,140 @@
+"""Drop-in for app/analyzers/video.py of the reference (same call, same return):
+
+    analyze(path: str, meta: dict) -> {"timeline": [...], "summary": {...}, "timeline_ai": <same list>}
+
+Host decode stays what the reference uses (cv2.VideoCapture: grab every frame, retrieve the sampled ones,
+video.py:11,27-34).  Everything computed per sampled frame runs on the B200 through libavd (engine.py);
+the O(samples) scalar tail (video.py:54-83) is float64 host arithmetic restated op for op.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from ._lib import REC_DTYPE, REC_HAS_FLOW, REC_HAS_PREV
+from .engine import default_engine
+
+#: sampled frames per host->device run when decoding a file (bounds pinned memory; one-sample halo between runs)
+DECODE_RUN = 48
+
+
+def sample_step(fps) -> int:
+    """video.py:19 -- ~2 analysed frames per second; Python round() is half-to-even (25 fps -> 12)."""
+    return max(1, int(round((fps or 30) / 2)))
+
+
+def _textures(recs: np.ndarray, npix: int) -> np.ndarray:
+    """float(Laplacian.var()) per sample from the exact integer sums (video.py:52)."""
+    s = recs["lap_sum"].astype(np.float64)
+    ss = recs["lap_sumsq"].astype(np.float64)
+    n = float(npix)
+    return (ss - s * s / n) / n
+
+
+def result_from_records(recs: np.ndarray, H: int, W: int, fps: float, duration: float, w=None, h=None) -> dict:
+    """Tail of video.analyze (video.py:54-83) from the per-sample records of one clip, in sample order.
+
+    recs[0] must be the clip's first sample (no predecessor); every later record carries flow statistics.
+    ``w``/``h`` are the values echoed in the summary (the reference echoes meta or cap.get values, :15-16,70).
+    """
+    recs = np.asarray(recs).view(REC_DTYPE).reshape(-1)
+    total = len(recs)
+    tex = _textures(recs, H * W)
+    has_flow = (recs["flags"] & REC_HAS_FLOW) != 0
+    flow_means = recs["flow_mean"][has_flow].astype(np.float64)
+    flow_vars = recs["flow_var"][has_flow].astype(np.float64)
+    # mot = flow_means[-1] if flow_means else 0.0   (video.py:55): the latest flow mean seen so far
+    if total:
+        idx = np.cumsum(has_flow) - 1
+        mot = np.where(idx >= 0, flow_means[np.maximum(idx, 0)] if len(flow_means) else 0.0, 0.0)
+        susp = np.clip(1.0 - (tex / (tex + 1000.0)) * (1.0 + mot), 0.0, 1.0)
+        timeline = [float(x) for x in susp]
+    else:
+        timeline = []
+    dup = int(np.count_nonzero(((recs["flags"] & REC_HAS_PREV) != 0) & (recs["ham_prev"] == 0)))
+    summary = {
+        "dup_density": float(dup / max(1, total - 1)),
+        "scene_change_rate": float(np.mean(flow_vars > 0.5)) if len(flow_vars) else 0.0,
+        "flow_mean": float(np.mean(flow_means)) if len(flow_means) else 0.0,
+        "flow_var": float(np.var(flow_means)) if len(flow_means) else 0.0,
+        "texture_var": float(np.var(tex)) if total else 0.0,
+        "w": int(W if w is None else w), "h": int(H if h is None else h), "fps": float(fps),
+    }
+    tlen = int(max(1, round(duration)))
+    if len(timeline) < tlen:
+        timeline = timeline + [timeline[-1]] * (tlen - len(timeline)) if timeline else [0.5] * tlen
+    else:
+        timeline = timeline[:tlen]
+    return {"timeline": timeline, "summary": summary, "timeline_ai": timeline}
+
+
+def records_from_frames(frames, engine=None) -> np.ndarray:
+    """Per-sample records of already-sampled frames (host arrays), through the streaming host entry point."""
+    eng = engine or default_engine()
+    return eng.analyze_host(frames)
+
+
+def analyze_frames(frames, meta: dict, engine=None) -> dict:
+    """Frames-level seam: ``frames`` are the *sampled* frames (what video.py:32 retrieves), in order.
+
+    meta: ``fps``, ``width``, ``height``, ``duration`` as in the reference (video.py:14-17); missing width /
+    height default to the frame shape, missing duration to len(frames)*step/fps.
+    """
+    n = len(frames)
+    fps = meta.get("fps") or 0.0
+    if n == 0:
+        return result_from_records(np.zeros(0, REC_DTYPE), 0, 0, fps, meta.get("duration") or 0.0,
+                                   w=meta.get("width") or 0, h=meta.get("height") or 0)
+    H, W = int(frames[0].shape[0]), int(frames[0].shape[1])
+    duration = meta.get("duration") or (n * sample_step(fps) / fps if fps > 0 else 0.0)
+    recs = records_from_frames(frames, engine)
+    return result_from_records(recs, H, W, fps, duration, w=meta.get("width") or W, h=meta.get("height") or H)
+
+
+def analyze(path: str, meta: dict, engine=None) -> dict:
+    """Same contract as the reference's video.analyze (video.py:10-83)."""
+    import cv2  # host decode only: the reference's own decoder
+    cap = cv2.VideoCapture(path)
+    if not cap.isOpened():
+        return {"timeline": [], "summary": {}, "timeline_ai": []}
+    fps = meta.get("fps") or cap.get(cv2.CAP_PROP_FPS) or 0.0
+    w = meta.get("width") or int(cap.get(cv2.CAP_PROP_FRAME_WIDTH) or 0)
+    h = meta.get("height") or int(cap.get(cv2.CAP_PROP_FRAME_HEIGHT) or 0)
+    duration = meta.get("duration") or (cap.get(cv2.CAP_PROP_FRAME_COUNT) / fps if fps > 0 else 0.0)
+    step = sample_step(fps)
+    eng = engine or default_engine()
+
+    runs, stage, fill, halo, shape = [], None, 0, None, None
+    index = 0
+
+    def flush():
+        nonlocal fill, halo
+        if fill == 0:
+            return
+        batch = [halo] + [stage[i] for i in range(fill)] if halo is not None else [stage[i] for i in range(fill)]
+        recs = eng.analyze_host(batch)
+        runs.append(recs[1:] if halo is not None else recs)
+        halo = stage[fill - 1].copy()
+        fill = 0
+
+    while True:
+        if not cap.grab():
+            break
+        if index % step == 0:
+            ok, frame = cap.retrieve()
+            if not ok:
+                break                                   # video.py:33: keep what we have
+            if stage is None:
+                shape = frame.shape
+                stage = eng.pinned((DECODE_RUN,) + tuple(shape))
+            if frame.shape != shape:
+                raise ValueError("frame size changed mid-stream")
+            np.copyto(stage[fill], frame)
+            fill += 1
+            if fill == DECODE_RUN:
+                flush()
+        index += 1
+    cap.release()
+    flush()
+    recs = np.concatenate(runs) if runs else np.zeros(0, REC_DTYPE)
+    H, W = (shape[0], shape[1]) if shape else (int(h), int(w))
+    return result_from_records(recs, H, W, fps, duration, w=w, h=h)

@@ -1,0 +1,298 @@
+#!/usr/bin/env python
+"""bench.py -- analyzed frames/sec of the per-frame analyzer hot path at 1080p (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+One step = one pass of the hot path over one batch of synthetic input:
+  N=1   BASELINE.json configs[1]: a 1080p 30 fps 60 s synthetic clip (1800 frames -> 120 sampled frames,
+        746 MB of BGR, larger than the 126 MB L2 so nothing is cache-resident between steps): K1 (per-frame
+        features) + K2 (119 Farneback pairs) + record read-back + the scalar tail (timeline, summary, fuse).
+  N>1   weak scaling: an N x 60 s clip, frame-chunk sharded -- every rank analyses 120 sampled frames plus a
+        one-sample halo, then one NCCL all-gather of the 160-byte records; rank 0 runs the tail.
+`value`   inputs resident in HBM when the timed region starts (device entry points of the C ABI).
+`e2e`     the same metric through the public host call (Engine.analyze_host -> avd_analyze_host): frames in
+          pinned host memory, host->device copies and record read-back inside the timed region.
+`roofline` K1 (the HBM-bound kernel north_star puts the >=90 % target on): algorithmic bytes = H*W*3 per
+          frame x frames per launch / mean launch duration from CUDA events on the launching
+          stream, against MEASURED_PEAKS.json.  K2 is compute/L2-bound; its per-kernel times are in `kernels`.
+`cpu_baseline` / --impl reference: the reference's per-sample body on the box's host cores (oracle/cv_body.py:
+          the same cv2/NumPy calls as video.py:36-57; /root/reference itself is not on the GPU box).
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+H, W, FPS, CLIP_FRAMES, SEED = 1080, 1920, 30.0, 1800, 1
+STEP = 15                              # video.py:19 at 30 fps
+SAMPLES = CLIP_FRAMES // STEP          # 120 analysed frames per 60 s clip
+FRAME_BYTES = H * W * 3
+
+
+def host_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def make_frames(rank: int, world: int, out: np.ndarray, halo_out):
+    """Sampled frames of this rank's 60 s chunk of the (world x 60 s) seed-1 clip, straight into `out`."""
+    import avd_b200.synth as synth
+    clip = synth.Clip(CLIP_FRAMES * world, H, W, SEED, fps=FPS)
+    first = rank * SAMPLES
+    for k in range(SAMPLES):
+        out[k] = clip[(first + k) * STEP]
+    if halo_out is not None:
+        halo_out[...] = clip[(first - 1) * STEP]
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler(threading.Thread):
+    """SM clock / throttle reasons during the timed region (NVML; nvidia-smi as a fallback)."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.stop_flag, self.samples, self.reasons, self.max_mhz = index, False, [], set(), None
+        self.nv = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def run(self):
+        names = {0x2: "applications_clocks_setting", 0x4: "sw_power_cap", 0x8: "hw_slowdown", 0x20: "sw_thermal_slowdown",
+                 0x40: "hw_thermal_slowdown", 0x80: "hw_power_brake_slowdown", 0x10: "sync_boost"}
+        while not self.stop_flag:
+            try:
+                if self.nv:
+                    self.samples.append(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM))
+                    r = self.nv.nvmlDeviceGetCurrentClocksEventReasons(self.h) if hasattr(self.nv, "nvmlDeviceGetCurrentClocksEventReasons") \
+                        else self.nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                    for bit, nm in names.items():
+                        if r & bit:
+                            self.reasons.add(nm)
+                else:
+                    import subprocess
+                    o = subprocess.run(["nvidia-smi", f"--id={self.index}", "--query-gpu=clocks.sm,clocks.max.sm,clocks_event_reasons.active",
+                                        "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout.split(",")
+                    self.samples.append(int(o[0])); self.max_mhz = int(o[1])
+            except Exception:
+                pass
+            time.sleep(0.05)
+
+    def result(self):
+        self.stop_flag = True
+        self.join(timeout=2)
+        s = sorted(self.samples)
+        return {"sm_mhz": (s[len(s) // 2] if s else None), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(s)}
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the reference's CPU path (cv2/NumPy port of video.py:36-57) on all host cores."""
+    if rank != 0:
+        return
+    from oracle import cv_body
+    cores = host_cores()
+    frames = np.empty((SAMPLES, H, W, 3), np.uint8)
+    make_frames(0, 1, frames, None)
+    pool = cv_body.Pool(frames, cores)
+    for _ in range(args.warmup):
+        pool.step()
+    t0 = time.perf_counter()
+    done = 0
+    for _ in range(args.steps):
+        done += pool.step()
+    dt = time.perf_counter() - t0
+    pool.close()
+    v = done / dt
+    line = {"impl": "reference", "metric": "analyzed frames/sec at 1080p", "value": v, "unit": "frames/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "u8/f32 (OpenCV)", "data": "synthetic",
+            "config": {"workload": "1080p 30fps 60s synthetic clip (1800 frames -> 120 sampled), per-frame features + flow + timeline",
+                       "frames_per_step": SAMPLES, "runs_on": "host CPU"},
+            "cpu_baseline": {"value": v, "unit": "frames/s", "cores": pool.procs, "kind": "port",
+                             "sample": f"{args.steps} x the full 120-sample clip, one process per core, cv2.setNumThreads(1), decode excluded"},
+            "e2e": {"value": v, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        return run_reference(args, rank, world)
+    assert args.warmup >= 3 or os.environ.get("AVD_BENCH_ALLOW_SHORT"), "timing rules: at least 3 warm-up steps"
+
+    # ---- synthetic input (host, before CUDA is touched so the CPU baseline may fork) ---------------------
+    host_frames = np.empty((SAMPLES, H, W, 3), np.uint8)
+    halo_np = np.empty((H, W, 3), np.uint8) if rank > 0 else None
+    make_frames(rank, world, host_frames, halo_np)
+
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        from oracle import cv_body
+        cores = host_cores()
+        pool = cv_body.Pool(host_frames, cores)
+        pool.step()                                        # warm (page-in, cv2 init)
+        t0 = time.perf_counter(); n_done = pool.step(); dt_all = time.perf_counter() - t0
+        pool.close()
+        t0 = time.perf_counter(); cv_body.run_chunk(host_frames[:16]); dt_one = time.perf_counter() - t0
+        cpu_baseline = {"value": n_done / dt_all, "unit": "frames/s", "cores": pool.procs, "kind": "port",
+                        "sample": "the full 120-sample clip once (after one warm pass), one process per core, cv2.setNumThreads(1), decode excluded",
+                        "single_process_value": 16 / dt_one}
+
+    # ---- GPU --------------------------------------------------------------------------------------------
+    import torch
+    import torch.distributed as dist
+    from avd_b200 import fusion, hints, video
+    from avd_b200 import dist as avd_dist
+    from avd_b200._lib import REC_DTYPE
+    from avd_b200.engine import Engine
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    eng = Engine(local_rank)
+    n_total = SAMPLES * world
+    meta = {"fps": FPS, "width": W, "height": H, "duration": CLIP_FRAMES * world / FPS, "bit_rate": 8_000_000}
+    hnt = hints.compute_hints(meta, "")
+
+    pinned = eng.pinned((SAMPLES + 1, H, W, 3))            # slot 0 = halo
+    pinned[1:] = host_frames
+    if halo_np is not None:
+        pinned[0] = halo_np
+    del host_frames
+    d_frames = torch.from_numpy(pinned[1:]).to(dev)
+    d_halo = torch.from_numpy(pinned[0]).to(dev) if rank > 0 else None
+    send_pad = torch.zeros((SAMPLES, REC_DTYPE.itemsize), dtype=torch.uint8, device=dev)
+    recv = torch.empty((world * SAMPLES, REC_DTYPE.itemsize), dtype=torch.uint8, device=dev) if world > 1 else None
+
+    def tail(recs_np):
+        res = video.result_from_records(recs_np, H, W, FPS, meta["duration"], w=W, h=H)
+        return fusion.fuse(fusion.neutral_audio(len(res["timeline"])), res, hnt)
+
+    def step_device():
+        rec = eng.analyze_device(d_frames, prev_frame=d_halo)
+        if world > 1:
+            dist.all_gather_into_tensor(recv, rec)
+            rec = recv
+        if rank == 0:
+            return tail(rec.cpu().numpy().view(REC_DTYPE).reshape(-1))
+        torch.cuda.current_stream().synchronize()
+        return None
+
+    host_batch = [pinned[i] for i in range(0 if rank > 0 else 1, SAMPLES + 1)]
+
+    def step_host():
+        recs = eng.analyze_host(host_batch)
+        if rank > 0:
+            recs = recs[1:]
+        if world > 1:
+            send_pad.copy_(torch.from_numpy(recs.view(np.uint8).reshape(SAMPLES, -1)))
+            dist.all_gather_into_tensor(recv, send_pad)
+            recs = recv.cpu().numpy().view(REC_DTYPE).reshape(-1) if rank == 0 else None
+        return tail(recs) if rank == 0 else None
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps, prof=False):
+        barrier()
+        if prof:
+            eng.profile_read(); eng.profile(True)
+        l0 = eng.launches
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        e0.record()
+        out = None
+        for _ in range(steps):
+            out = fn()
+        e1.record()
+        barrier()
+        wall = time.perf_counter() - t0
+        ms = max(e0.elapsed_time(e1), 0.0)
+        kern = None
+        if prof:
+            eng.profile(False); kern = eng.profile_read()
+        t = torch.tensor([max(ms / 1e3, wall)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item()), eng.launches - l0, kern, out
+
+    for _ in range(args.warmup):
+        step_device()
+    sampler = ClockSampler(local_rank); sampler.start()
+    dt, launches, _, result = timed(step_device, args.steps)
+    clocks = sampler.result()
+    # same loop again with per-launch CUDA events on (kept out of `value`: the events add ~1 us per launch)
+    _, _, kern, _ = timed(step_device, args.steps, prof=True)
+    for _ in range(args.warmup):
+        step_host()
+    dt_e2e, _, _, result_e2e = timed(step_host, args.steps)
+
+    if rank == 0:
+        value = n_total * args.steps / dt
+        hbm, hbm_src = peaks()
+        k1 = kern.get("k1_fused") or {"ms": sum(kern[k]["ms"] for k in ("gray", "lap", "area_h", "area_v", "area_int", "thumb") if k in kern),
+                                      "launches": kern.get("gray", {}).get("launches", 1)}
+        k1_name = "k1_fused" if "k1_fused" in kern else "k1_generic(gray+lap+area+thumb)"
+        frames_per_launch = (SAMPLES + (1 if d_halo is not None else 0)) * args.steps / max(1, k1["launches"])
+        k1_ms = k1["ms"] / max(1, k1["launches"])
+        achieved = FRAME_BYTES * frames_per_launch / (k1_ms * 1e-3) / 1e9
+        total_kernel_ms = sum(v["ms"] for v in kern.values())
+        line = {
+            "metric": "analyzed frames/sec at 1080p", "value": value, "unit": "frames/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "u8 (K1 integer path) / f32+f64 (Farneback)", "data": "synthetic",
+            "config": {"workload": "1080p 30fps 60s synthetic clip (1800 frames -> 120 sampled frames) per GPU: per-frame features + 119 flow pairs + timeline/fuse",
+                       "frames_per_step_per_gpu": SAMPLES, "sharding": "none" if world == 1 else f"frame-chunk x{world}, 1-sample halo, all-gather of 160 B records",
+                       "l2_policy": "inputs (746 MB/GPU) larger than L2 (126 MB), no flush needed", "seed": SEED},
+            "clocks": clocks, "gpu_launches": int(launches),
+            "e2e": {"value": n_total * args.steps / dt_e2e, "unit": "frames/s", "h2d_bytes_per_step": int(FRAME_BYTES * (SAMPLES * world + world - 1)),
+                    "d2h_bytes_per_step": int(160 * n_total), "ms_per_step": 1e3 * dt_e2e / args.steps},
+            "roofline": {"kernel": k1_name, "bound": "hbm", "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm,
+                         "traffic": None, "peak_source": hbm_src, "ms_per_launch": k1_ms, "frames_per_launch": frames_per_launch,
+                         "share_of_kernel_time": k1["ms"] / total_kernel_ms if total_kernel_ms else None},
+            "kernels": {k: {"ms_per_step": v["ms"] / args.steps, "launches_per_step": v["launches"] / args.steps} for k, v in sorted(kern.items())},
+            "k2_us_per_pair": 1e3 * sum(v["ms"] for k, v in kern.items() if k in ("pyr", "polyexp", "update_matrices", "blur_solve", "magstats")) / args.steps / (SAMPLES - (0 if d_halo is not None else 1)),
+            "cpu_baseline": cpu_baseline,
+            "result": {"ai_score": result["result"]["ai_score"], "label": result["result"]["label"],
+                       "e2e_matches_device": result_e2e == result},
+        }
+        print(json.dumps(line), flush=True)
+    eng.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

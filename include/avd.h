@@ -1,0 +1,129 @@
+/*
+ * avd.h -- C ABI of libavd.so, the B200 (sm_100a) implementation of the per-frame analyzer hot path of
+ * backtato/ai-video-detector.
+ *
+ * The reference has no FFI: its seam is the Python call  video_an.analyze(path, meta)  (api.py:133,
+ * defined at app/analyzers/video.py:10).  Everything that call computes per sampled frame is a library
+ * call into OpenCV/NumPy; the entry points below replace exactly those calls and are what a maintainer
+ * binds with ctypes (INTEGRATION.md shows the stub).  Each entry cites the reference lines it replaces.
+ *
+ * Conventions: plain pointers and sizes, no C++/torch types; every function returns 0 on success or a
+ * negative avd_status, never throws, never aborts; the message for the last failure on a context is
+ * avd_last_error(ctx).  The caller owns every buffer it passes; the library owns its streams, staging
+ * rings and workspaces.  "d_" pointers are device memory on the context's device, "h_" pointers are host
+ * memory (pinned for full PCIe rate: avd_host_alloc).  `stream` is a cudaStream_t passed as void* (NULL =
+ * the context's own compute stream); device-pointer entry points are asynchronous on that stream.
+ * A context may be used by one thread at a time; create one per (thread, device) (api.py:133 runs the
+ * analyzer on pool threads).
+ */
+#ifndef AVD_H
+#define AVD_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define AVD_THUMB 320      /* video.py:43  resize(..., (320,320)) */
+#define AVD_HASH_SIDE 32   /* video.py:36  _average_hash(frame, size=32) */
+
+typedef enum avd_status {
+    AVD_OK = 0,
+    AVD_ERR_ARG = -1,       /* bad argument (NULL, n < 0, H or W < 32, pitch too small, ...) */
+    AVD_ERR_CUDA = -2,      /* a CUDA runtime call or kernel failed; see avd_last_error */
+    AVD_ERR_NOMEM = -3,     /* device or pinned allocation failed */
+    AVD_ERR_NODEVICE = -4   /* no usable sm_100 device */
+} avd_status;
+
+typedef struct avd_ctx avd_ctx;
+
+/* One record per sampled frame: everything video.py:36-52 derives from that frame (and its predecessor).
+ * 160 bytes; also the element of the multi-GPU all-gather. */
+typedef struct avd_sample_rec {
+    int64_t  lap_sum;      /* sum   of cv2.Laplacian(gray, CV_64F)            video.py:52 */
+    int64_t  lap_sumsq;    /* sum of squares of the same; var = (ss - s*s/N)/N video.py:52 */
+    float    flow_mean;    /* float(np.mean(mag)) vs previous sample           video.py:47 ; 0 if none */
+    float    flow_var;     /* float(np.var(mag))                               video.py:48 ; 0 if none */
+    uint32_t hash[32];     /* (g >= g.mean()) bit i&31 of word i>>5, i=row*32+col  video.py:4-8 */
+    int32_t  ham_prev;     /* int(np.sum(hsh ^ prev_hash)); -1 if no predecessor   video.py:38 */
+    uint32_t flags;        /* bit0: has predecessor hash; bit1: has flow stats */
+} avd_sample_rec;
+
+#define AVD_REC_HAS_PREV 1u
+#define AVD_REC_HAS_FLOW 2u
+
+const char *avd_version(void);
+int  avd_device_count(void);
+
+int  avd_create(int device, avd_ctx **out);
+void avd_destroy(avd_ctx *ctx);
+const char *avd_last_error(const avd_ctx *ctx);
+int  avd_sync(avd_ctx *ctx);                         /* waits for all work of the context */
+
+/* pinned host memory for frame batches (cudaHostAlloc) */
+void *avd_host_alloc(avd_ctx *ctx, size_t bytes);
+void  avd_host_free(avd_ctx *ctx, void *p);
+
+/*
+ * K1 -- per-frame features of n BGR frames resident in HBM.   Replaces, per frame:
+ *   cv2.cvtColor(BGR2GRAY)                       video.py:5,43,51
+ *   cv2.resize(g,(32,32),INTER_AREA) + g>=mean   video.py:6-8      -> rec.hash   (d_area32: the 32x32 u8, optional)
+ *   int(np.sum(hsh ^ prev_hash))                 video.py:38       -> rec.ham_prev
+ *   cv2.resize(gray,(320,320))                   video.py:43       -> d_thumbs[i] (320*320 u8)
+ *   cv2.Laplacian(gray,CV_64F) sums              video.py:52       -> rec.lap_sum / lap_sumsq
+ * Frame i starts at d_bgr + i*frame_stride, row y at + y*row_pitch, pixel = B,G,R bytes.
+ * d_prev_hash: 32 words of the sample before frame 0 (chunk halo), or NULL.
+ * Writes all fields of d_rec[0..n) (flow fields zeroed).
+ */
+int avd_frames_features(avd_ctx *ctx, const uint8_t *d_bgr, int n, int H, int W, size_t row_pitch,
+                        size_t frame_stride, const uint32_t *d_prev_hash, avd_sample_rec *d_rec,
+                        uint8_t *d_thumbs, uint8_t *d_area32, void *stream);
+
+/*
+ * K2 -- Farneback flow magnitude statistics between consecutive thumbnails.   Replaces
+ *   cv2.calcOpticalFlowFarneback(prev, small, None, 0.5, 3, 15, 3, 5, 1.2, 0)   video.py:45
+ *   mag = sqrt(fx^2+fy^2); np.mean(mag); np.var(mag)                              video.py:46-48
+ * for the pairs (d_thumbs[i-1], d_thumbs[i]), i = 1..n-1, and, if d_prev_thumb != NULL, the pair
+ * (d_prev_thumb, d_thumbs[0]).  Results go to d_rec[i].flow_mean / flow_var and flags |= HAS_FLOW.
+ */
+int avd_flow_stats(avd_ctx *ctx, const uint8_t *d_thumbs, int n, const uint8_t *d_prev_thumb,
+                   avd_sample_rec *d_rec, void *stream);
+
+/* Parity/debug: the dense flow fields themselves.  Pair p = (d_prev + p*102400, d_next + p*102400);
+ * d_flow[p] is 320 x 320 x 2 float32 (x,y interleaved, the layout cv2 returns). */
+int avd_flow_fields(avd_ctx *ctx, const uint8_t *d_prev, const uint8_t *d_next, int n_pairs,
+                    float *d_flow, void *stream);
+
+/* Parity/debug: the gray plane of one device-resident frame (H*W u8, dense). */
+int avd_gray(avd_ctx *ctx, const uint8_t *d_bgr, int H, int W, size_t row_pitch, uint8_t *d_gray, void *stream);
+
+/*
+ * Whole hot path from host memory -- what video.analyze's sampled-frame loop (video.py:31-52) does for
+ * a run of n sampled frames.  h_frames[i] points at frame i (H rows of row_pitch bytes).  Frames are
+ * streamed to the device in chunks on a copy stream while K1/K2 run on the compute stream; records come
+ * back to h_rec[0..n).  For a chunk of a longer clip (multi-GPU frame-chunk sharding, or host-side
+ * streaming of a long clip) the caller passes the sample *before* the chunk as frame 0 (one-sample halo)
+ * and drops h_rec[0].  Synchronous: returns when h_rec is complete.
+ */
+int avd_analyze_host(avd_ctx *ctx, const uint8_t *const *h_frames, int n, int H, int W, size_t row_pitch,
+                     avd_sample_rec *h_rec);
+
+/* Counters for bench.py: number of kernel launches issued by this context since creation. */
+uint64_t avd_launch_count(const avd_ctx *ctx);
+
+/* Per-kernel device timing for bench.py: when enabled, every launch is bracketed by CUDA events on its
+ * stream.  avd_profile_read synchronises, writes JSON {"kernel": {"ms": total, "launches": n}, ...} to buf
+ * and clears the log. */
+int avd_profile_enable(avd_ctx *ctx, int on);
+int avd_profile_read(avd_ctx *ctx, char *buf, size_t cap);
+
+/* Select the per-frame kernel: 0 = auto (fused TMA path when W % 16 == 0 and buffers are 16-byte
+ * aligned, generic otherwise), 1 = force generic multi-kernel path.  For tests. */
+int avd_set_k1_mode(avd_ctx *ctx, int mode);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AVD_H */

@@ -1,0 +1,182 @@
+"""CPU: host-side mirror of the reference interface (video tail, hints, fusion), the C-ABI surface, and the
+sharding logic over gloo (world_size 2).  No GPU compute."""
+import copy
+import ctypes as C
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from conftest import FLOW_ATOL, ROOT, close
+
+
+def _records_from_golden(c):
+    from avd_b200._lib import REC_DTYPE
+    n = c["n_samples"]
+    r = np.zeros(n, REC_DTYPE)
+    r["lap_sum"], r["lap_sumsq"] = c["lap_sum"], c["lap_sumsq"]
+    r["flow_mean"][1:] = [m for m, _ in c["flow_stats"]]
+    r["flow_var"][1:] = [v for _, v in c["flow_stats"]]
+    r["flags"][1:] = 3
+    r["ham_prev"][0] = -1
+    r["ham_prev"][1:] = c.get("ham", [7] * (n - 1))
+    r["hash"] = np.array(c["hash_words"], np.uint32)
+    return r
+
+
+def _same_result(out, ref, tex_rtol=1e-12):
+    assert out["timeline"] is out["timeline_ai"]                     # video.py:83 returns one list twice
+    assert len(out["timeline"]) == len(ref["timeline"])
+    assert all(isinstance(x, float) for x in out["timeline"])        # JSON-serialisable plain floats
+    for a, b in zip(out["timeline"], ref["timeline"]):
+        assert abs(a - b) <= 1e-12 + tex_rtol * abs(b)
+    for k, b in ref["summary"].items():
+        a = out["summary"][k]
+        assert type(a) is type(b)
+        if isinstance(b, int) or k in ("dup_density", "scene_change_rate", "fps"):
+            assert a == b, k
+        else:
+            assert abs(a - b) <= 1e-10 * abs(b), (k, a, b)
+
+
+@pytest.mark.parametrize("name", ["clip_small", "clip_odd", "clip_nometa", "clip_720p", "clip_1080p_head"])
+def test_video_tail_matches_reference(golden, name):
+    from avd_b200 import video
+    c = golden["clips"][name]
+    dur = c["meta"].get("duration") or c["n_frames"] / c["fps"]
+    out = video.result_from_records(_records_from_golden(c), c["H"], c["W"], c["fps"], dur)
+    _same_result(out, c["result"])
+
+
+def test_video_tail_edge_cases():
+    from avd_b200 import video
+    from avd_b200._lib import REC_DTYPE
+    r = video.result_from_records(np.zeros(0, REC_DTYPE), 0, 0, 0.0, 0.0)        # nothing decoded
+    assert r["timeline"] == [0.5] and r["summary"]["dup_density"] == 0.0 and r["summary"]["flow_mean"] == 0.0
+    one = np.zeros(1, REC_DTYPE); one["lap_sumsq"] = 100 * 64 * 64; one["ham_prev"] = -1
+    r = video.result_from_records(one, 64, 64, 30.0, 3.4)                        # one sample, padded to round(3.4)=3
+    assert len(r["timeline"]) == 3 and r["timeline"][0] == r["timeline"][2] == 1.0 - 100.0 / 1100.0
+    assert video.sample_step(25) == 12 and video.sample_step(None) == 15 and video.sample_step(1) == 1
+    assert video.result_from_records(np.zeros(0, REC_DTYPE), 0, 0, 0.0, 2.5)["timeline"] == [0.5, 0.5]   # round half even
+
+
+def test_analyze_unopenable_path_returns_reference_shape():
+    from avd_b200 import video
+    assert video.analyze("/nonexistent/clip.mp4", {}) == {"timeline": [], "summary": {}, "timeline_ai": []}   # video.py:12-13
+
+
+def test_fusion_and_hints_match_reference(golden):
+    from avd_b200 import fusion, hints
+    for c in golden["fuse"]:
+        audio, video = copy.deepcopy(c["audio"]), copy.deepcopy(c["video"])
+        assert hints.compute_hints(c["meta"], "x") == c["hints"]
+        assert fusion.fuse(audio, video, c["hints"]) == c["out"]
+        assert audio["timeline"] == c["audio_timeline_after"] and video["timeline"] == c["video_timeline_after"]
+
+
+def test_fusion_score_rounding_gate(golden):
+    from avd_b200 import fusion
+    c = golden["fuse"][3]
+    out = fusion.fuse(copy.deepcopy(c["audio"]), copy.deepcopy(c["video"]), c["hints"], with_raw=True)
+    assert abs(out["_raw_score"] - c["out"]["result"]["ai_score"]) <= 0.005 + 1e-12
+
+
+def test_c_abi_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, "include", "avd.h")).read()
+    declared = set(re.findall(r"\b(avd_[a-z0-9_]+)\s*\(", hdr))
+    from avd_b200 import _lib
+    assert declared == set(_lib.SYMBOLS), declared ^ set(_lib.SYMBOLS)
+    so = _lib.LIB_PATH
+    if not os.path.exists(so):
+        import __graft_entry__ as g
+        g.build()
+    L = C.CDLL(so)
+    for s in declared:
+        assert hasattr(L, s), s
+    assert b"sm_100a" in _lib.load().avd_version()
+    # the SASS in the library is sm_100a only
+    out = subprocess.run(["cuobjdump", "-lelf", so], capture_output=True, text=True).stdout
+    assert "sm_100a" in out and "sm_90" not in out
+
+
+def test_no_cpu_fallback_without_gpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from avd_b200._lib import AvdError
+    from avd_b200.engine import Engine
+    with pytest.raises(AvdError):
+        Engine(0)
+    from avd_b200 import video
+    with pytest.raises(AvdError):
+        video.analyze_frames([np.zeros((64, 64, 3), np.uint8)], {"fps": 30.0})
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "ai-video-detector_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".h", ".cpp")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle|liboracle|#include.*oracle|dlopen", src, re.M), \
+                    f"{f} reaches into oracle/"
+
+
+def test_shard_bounds():
+    from avd_b200 import dist
+    assert [hi - lo for lo, hi in dist.shard_bounds(60, 8)] == [8, 8, 8, 8, 7, 7, 7, 7]
+    assert dist.shard_bounds(3, 4) == [(0, 1), (1, 2), (2, 3), (3, 3)]
+    assert dist.local_range_with_halo(120, 0, 2) == (0, 60, None)
+    assert dist.local_range_with_halo(120, 1, 2) == (60, 120, 59)
+    assert dist.local_range_with_halo(3, 3, 4) == (3, 3, None)
+    assert list(dist.shard_clips(256, 7, 8)) == list(range(224, 256))
+
+
+_WORKER = r"""
+import os, sys, json, numpy as np
+sys.path.insert(0, {root!r})
+import torch.distributed as dist
+from avd_b200 import dist as avd_dist, video
+from avd_b200._lib import REC_DTYPE
+import avd_b200.synth as synth
+from oracle import oracle as O
+
+def records_fn(frames):       # CPU stand-in for Engine.analyze_host: same record layout, oracle arithmetic
+    out = np.zeros(len(frames), REC_DTYPE)
+    for i, r in enumerate(O.frames_features(frames)):
+        out[i]["lap_sum"], out[i]["lap_sumsq"] = r["lap_sum"], r["lap_sumsq"]
+        out[i]["hash"] = r["hash"]; out[i]["ham_prev"] = r["ham"]; out[i]["flags"] = 1 if r["ham"] >= 0 else 0
+        if "flow_mean" in r:
+            out[i]["flow_mean"], out[i]["flow_var"] = r["flow_mean"], r["flow_var"]; out[i]["flags"] |= 2
+    return out
+
+rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+dist.init_process_group("gloo", rank=rank, world_size=world)
+clip = synth.Clip(105, 96, 128, seed=31, fps=30.0)
+frames = clip.sampled(15)                      # 7 samples -> shards 4 + 3
+meta = {{"fps": 30.0, "width": 128, "height": 96, "duration": 3.5}}
+lo, hi, halo = avd_dist.local_range_with_halo(len(frames), rank, world)
+res, full = avd_dist.analyze_frames_sharded(frames[lo:hi], frames[halo] if halo is not None else None,
+                                            len(frames), meta, rank, world, records_fn)
+single = records_fn(list(frames))
+assert full.tobytes() == single.tobytes(), "sharded records differ from the single-process run"
+want = video.result_from_records(single, 96, 128, 30.0, 3.5)
+assert res == want
+if rank == 0:
+    print("SHARD_OK", json.dumps(res["summary"]))
+dist.destroy_process_group()
+"""
+
+
+def test_frame_chunk_sharding_world2_gloo(tmp_path):
+    script = tmp_path / "w.py"
+    script.write_text(_WORKER.format(root=ROOT))
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT="29531", WORLD_SIZE="2")
+    procs = [subprocess.Popen([sys.executable, str(script)], env=dict(env, RANK=str(r)), stdout=subprocess.PIPE,
+                              stderr=subprocess.STDOUT, text=True) for r in range(2)]
+    outs = [p.communicate(timeout=240)[0] for p in procs]
+    assert all(p.returncode == 0 for p in procs), outs
+    assert "SHARD_OK" in outs[0]
