@@ -264,7 +264,7 @@ int avd_frames_features(avd_ctx *ctx, const uint8_t *d_bgr, int n, int H, int W,
     if (n == 0) return AVD_OK;
     if (!d_bgr || !d_rec || !d_thumbs || frame_stride < row_pitch * (size_t)H) { ctx->err = "null buffer or frame_stride < H*row_pitch"; return AVD_ERR_ARG; }
     AVD_CUDA(ctx, cudaSetDevice(ctx->device));
-    cudaStream_t st = stream ? (cudaStream_t)stream : ctx->compute;
+    cudaStream_t st = (cudaStream_t)stream;   // NULL is CUDA's default stream, as for any cudaStream_t
     const ShapeTables *tab, *htab;
     if ((rc = avd_get_tables(ctx, H, W, &tab, &htab))) return rc;
     if (!d_area32) {
@@ -287,7 +287,7 @@ int avd_flow_stats(avd_ctx *ctx, const uint8_t *d_thumbs, int n, const uint8_t *
     if (n == 0) return AVD_OK;
     if (!d_thumbs || !d_rec) { ctx->err = "null buffer"; return AVD_ERR_ARG; }
     AVD_CUDA(ctx, cudaSetDevice(ctx->device));
-    cudaStream_t st = stream ? (cudaStream_t)stream : ctx->compute;
+    cudaStream_t st = (cudaStream_t)stream;   // NULL is CUDA's default stream, as for any cudaStream_t
     int n_pairs = d_prev_thumb ? n : n - 1;
     return k2_flow(ctx, d_prev_thumb, d_thumbs, 0, (size_t)AVD_T * AVD_T, n_pairs, true,
                    d_prev_thumb ? d_rec : d_rec + 1, nullptr, st);
@@ -299,7 +299,7 @@ int avd_flow_fields(avd_ctx *ctx, const uint8_t *d_prev, const uint8_t *d_next, 
     if (n_pairs == 0) return AVD_OK;
     if (!d_prev || !d_next || !d_flow) { ctx->err = "null buffer"; return AVD_ERR_ARG; }
     AVD_CUDA(ctx, cudaSetDevice(ctx->device));
-    cudaStream_t st = stream ? (cudaStream_t)stream : ctx->compute;
+    cudaStream_t st = (cudaStream_t)stream;   // NULL is CUDA's default stream, as for any cudaStream_t
     return k2_flow(ctx, d_prev, d_next, (size_t)AVD_T * AVD_T, (size_t)AVD_T * AVD_T, n_pairs, false, nullptr, d_flow, st);
 }
 
@@ -310,7 +310,7 @@ int avd_gray(avd_ctx *ctx, const uint8_t *d_bgr, int H, int W, size_t row_pitch,
     if (rc) return rc;
     if (!d_bgr || !d_gray) { ctx->err = "null buffer"; return AVD_ERR_ARG; }
     AVD_CUDA(ctx, cudaSetDevice(ctx->device));
-    return k1_gray_only(ctx, d_bgr, H, W, row_pitch, d_gray, stream ? (cudaStream_t)stream : ctx->compute);
+    return k1_gray_only(ctx, d_bgr, H, W, row_pitch, d_gray, (cudaStream_t)stream);
 }
 
 // Host streaming pipeline.  Frames go to a ring of device slots on the copy stream; K1 consumes a slot on

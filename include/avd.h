@@ -12,7 +12,7 @@
  * avd_last_error(ctx).  The caller owns every buffer it passes; the library owns its streams, staging
  * rings and workspaces.  "d_" pointers are device memory on the context's device, "h_" pointers are host
  * memory (pinned for full PCIe rate: avd_host_alloc).  `stream` is a cudaStream_t passed as void* (NULL =
- * the context's own compute stream); device-pointer entry points are asynchronous on that stream.
+ * CUDA's default stream, as usual); device-pointer entry points are asynchronous on that stream.
  * A context may be used by one thread at a time; create one per (thread, device) (api.py:133 runs the
  * analyzer on pool threads).
  */
