@@ -4,10 +4,14 @@
 // HBM traffic = H*W*3 bytes read once + 102400 + 1024 + 16 bytes written per frame.
 //
 // Decomposition: CTA = (frame, band b), band b = the source rows of INTER_AREA destination row b
-// (H/32 rows plus one halo row above and below for the Laplacian / fractional cell taps).  Rows stream
-// through shared memory with TMA bulk copies (cp.async.bulk -> UBLKCP) on an mbarrier ring; each thread
-// owns a 16-pixel column strip (48 bytes = 3 conflict-free LDS.128) and marches down the band keeping
-// the previous two gray rows in registers, so the Laplacian needs no second read of anything.
+// (H/32 rows plus one halo row above and below for the Laplacian / fractional cell taps).
+//   producer warp   one lane streams the band's rows into a ring of single-row shared-memory stages with
+//                   TMA bulk copies (cp.async.bulk -> UBLKCP), full/empty mbarriers per stage
+//   consumer warps  each thread owns a 16-pixel column strip (48 bytes = 3 conflict-free LDS.128) and
+//                   marches down the band two rows at a time, keeping the previous rows in registers
+//                   (two alternating register sets, so no register shuffling), writes packed gray to a
+//                   small ring; every 4 rows all consumers meet once (named barrier) and then run the
+//                   resampling passes (INTER_AREA row partials, thumbnail rows) out of the gray ring.
 //
 // Instruction budget: at 6.5 TB/s an SM has ~16 issue slots per pixel, so the arithmetic is packed:
 //   gray        2 IDP.2A per pixel on 16-bit weights doubled so that Y lands in byte 2 of the accumulator
@@ -19,10 +23,10 @@
 
 namespace {
 
-constexpr int CH = 2;                 // rows per TMA stage
-constexpr int NSTAGE = 2;             // stages in flight per CTA (several CTAs per SM overlap)
-constexpr int GR = 4;                 // rows per resample group (multiple of CH)
-constexpr int RC = GR + CH + 1;       // gray ring rows: group + carry row + first chunk of the next group
+constexpr int NRS = 4;                // single-row TMA stages in flight per CTA
+constexpr int GR = 4;                 // rows per resample group (two row pairs)
+constexpr int RC = 2 * GR + 1;        // gray ring rows: previous group + carry row + group being written
+constexpr int MAX_TY = 32;            // thumbnail rows one band can own
 
 struct K1Params {
     const uint8_t *bgr;
@@ -31,7 +35,8 @@ struct K1Params {
     const ShapeTables *tab;
     avd_sample_rec *rec;
     uint8_t *thumbs, *area32;
-    int area_aligned;                 // W % 128 == 0: INTER_AREA cells are whole aligned words
+    int area_aligned;                 // INTER_AREA cells are whole aligned words in x
+    int max_cell_rows;
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -43,10 +48,14 @@ __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes)
 {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
-__device__ __forceinline__ void tma_load_1d(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar)
+__device__ __forceinline__ void mbar_arrive(uint32_t bar)
 {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tma_load_1d(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar, uint64_t policy)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar), "l"(policy) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
 {
@@ -60,6 +69,7 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
         "DONE:\n"
         "}" ::"r"(bar), "r"(parity) : "memory");
 }
+__device__ __forceinline__ void consumer_sync(int n) { asm volatile("bar.sync 1, %0;" ::"r"(n) : "memory"); }
 
 // 2*(3735,19235,9798): the doubled 15-bit weights; acc = 2*(...)+32768 so gray = acc >> 16 = byte 2
 constexpr uint32_t WB = 7470u, WG = 38470u, WR = 19596u;
@@ -77,19 +87,57 @@ __device__ __forceinline__ void gray4(uint32_t w0, uint32_t w1, uint32_t w2, uin
 }
 
 struct LapAcc { uint32_t s, ll, hl, hh; };
+// one gray row of a 16-pixel strip: even/odd pixels in 16-bit lanes, and base = left+right-4*centre+1020
+struct RowSet { uint32_t E[4], O[4], BE[4], BO[4]; };
 
-// biased Laplacian of 4 pixels (two 16-bit-lane registers) and its statistics
-__device__ __forceinline__ void lap4(uint32_t he, uint32_t ho, uint32_t ec, uint32_t oc, uint32_t eu, uint32_t ou,
-                                     uint32_t ed, uint32_t od, LapAcc &A)
+// biased Laplacian (L+1020 in [0,2040] per 16-bit lane) of the centre row and its statistics
+__device__ __forceinline__ void lap_row(const RowSet &c, const RowSet &u, const RowSet &d, LapAcc &A)
 {
-    uint32_t le = he + eu + ed + KBIAS - 4u * ec;            // lanes: L + 1020 in [0, 2040]
-    uint32_t lo = ho + ou + od + KBIAS - 4u * oc;
-    A.s = __dp2a_lo(le, 0x0101u, A.s);
-    A.s = __dp2a_lo(lo, 0x0101u, A.s);
-    uint32_t pl = __byte_perm(le, lo, 0x6420), ph = __byte_perm(le, lo, 0x7531);
-    A.ll = __dp4a(pl, pl, A.ll);
-    A.hl = __dp4a(ph, pl, A.hl);
-    A.hh = __dp4a(ph, ph, A.hh);
+#pragma unroll
+    for (int g = 0; g < 4; g++) {
+        uint32_t le = c.BE[g] + u.E[g] + d.E[g];
+        uint32_t lo = c.BO[g] + u.O[g] + d.O[g];
+        A.s = __dp2a_lo(le, 0x0101u, A.s);
+        A.s = __dp2a_lo(lo, 0x0101u, A.s);
+        uint32_t pl = __byte_perm(le, lo, 0x6420), ph = __byte_perm(le, lo, 0x7531);
+        A.ll = __dp4a(pl, pl, A.ll);
+        A.hl = __dp4a(ph, pl, A.hl);
+        A.hh = __dp4a(ph, ph, A.hh);
+    }
+}
+
+// convert one staged BGR row strip to gray: fills the row set and stores the 16 packed gray bytes
+__device__ __forceinline__ void load_row(const uint8_t *sp, uint8_t *gdst, bool first, bool last, RowSet &R)
+{
+    const uint4 q0 = *(const uint4 *)sp, q1 = *(const uint4 *)(sp + 16), q2 = *(const uint4 *)(sp + 32);
+    const uint32_t wl = *(const uint32_t *)(sp - 4), wr = *(const uint32_t *)(sp + 48);
+    uint32_t a[16];
+    gray4(q0.x, q0.y, q0.z, a[0], a[1], a[2], a[3]);
+    gray4(q0.w, q1.x, q1.y, a[4], a[5], a[6], a[7]);
+    gray4(q1.z, q1.w, q2.x, a[8], a[9], a[10], a[11]);
+    gray4(q2.y, q2.z, q2.w, a[12], a[13], a[14], a[15]);
+    // neighbour pixels x-1 and x+16 (REFLECT_101 at the frame edges: x=-1 -> 1, x=W -> W-2)
+    uint32_t aL = __dp2a_hi(C_GR, wl, __dp2a_lo(C_0B, wl, RND));
+    uint32_t aR = __dp2a_hi(C_R0, wr, __dp2a_lo(C_BG, wr, RND));
+    aL = first ? a[1] : aL;
+    aR = last ? a[14] : aR;
+#pragma unroll
+    for (int g = 0; g < 4; g++) {
+        R.E[g] = __byte_perm(a[4 * g], a[4 * g + 2], 0x7632);       // (g0, g2) in 16-bit lanes
+        R.O[g] = __byte_perm(a[4 * g + 1], a[4 * g + 3], 0x7632);   // (g1, g3)
+    }
+    uint4 gw;
+    gw.x = __byte_perm(R.E[0], R.O[0], 0x6240); gw.y = __byte_perm(R.E[1], R.O[1], 0x6240);
+    gw.z = __byte_perm(R.E[2], R.O[2], 0x6240); gw.w = __byte_perm(R.E[3], R.O[3], 0x6240);
+    *(uint4 *)gdst = gw;
+#pragma unroll
+    for (int g = 0; g < 4; g++) {
+        // left neighbours of (g0,g2) are (gL,g1); right neighbours of (g1,g3) are (g2,gR)
+        uint32_t el = g == 0 ? __byte_perm(aL, R.O[0], 0x5432) : __byte_perm(R.O[g - 1], R.O[g], 0x5432);
+        uint32_t orr = g == 3 ? __byte_perm(R.E[3], aR, 0x7632) : __byte_perm(R.E[g], R.E[g + 1], 0x5432);
+        R.BE[g] = el + R.O[g] + KBIAS - 4u * R.E[g];
+        R.BO[g] = R.E[g] + orr + KBIAS - 4u * R.O[g];
+    }
 }
 
 __device__ __forceinline__ uint8_t sat_rne(float v)
@@ -104,176 +152,202 @@ __device__ __forceinline__ float mulbyte(uint32_t word, uint32_t sel, float alph
     return __fmaf_rn(__uint_as_float(__byte_perm(word, 0x4B000000u, sel)), alpha, nbias);
 }
 
-__global__ void __launch_bounds__(256) k1_fused_kernel(K1Params P)
+struct Band {
+    int own0, own1, lo, hi, H, W, cons;   // cons = consumer threads
+    uint32_t bar_full, bar_empty;
+    const uint8_t *stage;
+    uint8_t *ring;
+    int row_bytes;
+};
+
+// rows (r0, r0+1) of the band: p0/p1 hold rows r0-2, r0-1; c0/c1 receive rows r0, r0+1
+__device__ __forceinline__ void pair_step(const Band &B, int i0, int r0, bool have1, int slot0, int slot1, int tid, bool active,
+                                          bool first, bool last, const RowSet &p0, const RowSet &p1, RowSet &c0, RowSet &c1, LapAcc &A)
+{
+    const int s0 = i0 % NRS, s1 = (i0 + 1) % NRS;
+    mbar_wait(B.bar_full + 8 * s0, (uint32_t)((i0 / NRS) & 1));
+    if (active) load_row(B.stage + s0 * B.row_bytes + 48 * tid, B.ring + slot0 * B.W + 16 * tid, first, last, c0);
+    if (have1) {
+        mbar_wait(B.bar_full + 8 * s1, (uint32_t)(((i0 + 1) / NRS) & 1));
+        if (active) load_row(B.stage + s1 * B.row_bytes + 48 * tid, B.ring + slot1 * B.W + 16 * tid, first, last, c1);
+    }
+    __syncwarp();
+    if ((tid & 31) == 0) {                       // this warp is done with both stages: hand them back to the producer
+        mbar_arrive(B.bar_empty + 8 * s0);
+        if (have1) mbar_arrive(B.bar_empty + 8 * s1);
+    }
+    if (!active) return;
+    const int cr = r0 - 1;                       // row r0-1 is now complete (down neighbour = c0)
+    if (cr >= B.own0 && cr < B.own1) lap_row(p1, p0, c0, A);
+    if (have1) {
+        if (r0 >= B.own0 && r0 < B.own1) {
+            if (r0 == 0) lap_row(c0, c1, c1, A);  // top frame edge: row -1 reflects to row 1
+            else lap_row(c0, p1, c1, A);
+        }
+        if (r0 + 1 == B.H - 1 && r0 + 1 < B.own1) lap_row(c1, c0, c0, A);   // bottom frame edge: row H reflects to H-2
+    } else if (r0 == B.H - 1 && r0 < B.own1) {
+        lap_row(c0, p1, p1, A);
+    }
+}
+
+template <int MAXT, int MINB>
+__global__ void __launch_bounds__(MAXT, MINB) k1_fused_kernel(K1Params P)
 {
     extern __shared__ __align__(128) uint8_t smem[];
-    const int tid = threadIdx.x, nt = blockDim.x;
+    const int tid = threadIdx.x;
+    const int cons = blockDim.x - 32;            // consumer threads; the last warp is the TMA producer
     const int b = blockIdx.x, f = blockIdx.y;
     const ShapeTables *__restrict__ tab = P.tab;
     const int H = P.H, W = P.W;
     const int own0 = tab->row_owner_begin[b], own1 = tab->row_owner_begin[b + 1];
     const int lo = max(own0 - 1, 0), hi = min(own1, H - 1);
-    const int nchunks = (hi - lo + 1 + CH - 1) / CH;
-    const int stage_bytes = CH * P.row_bytes;
-    uint8_t *stage = smem + 128;
-    uint8_t *ring = stage + NSTAGE * stage_bytes;
-    float *rowbuf = (float *)(ring + RC * W);
-    const uint32_t bar0 = smem_u32(smem);
-    const uint8_t *src = P.bgr + (size_t)f * P.fstride;
-    const AreaCell cy = tab->ay[b];
-    const int cell_lo = cy.has_head ? cy.s1 - 1 : cy.s1, cell_hi = cy.has_tail ? cy.s2 : cy.s2 - 1;
-    const int area_int = tab->area_int;
+    const int nrows = hi - lo + 1;
+    // shared memory carve-up
+    uint8_t *stage = smem + 128;                                   // NRS rows of BGR
+    uint8_t *ring = stage + NRS * P.row_bytes;                     // RC rows of gray
+    float *rowbuf = (float *)(ring + RC * W);                      // INTER_AREA row partials [cell rows][32]
+    uint2 *xt = (uint2 *)(rowbuf + P.max_cell_rows * 32);          // packed x taps of the thumbnail [320]
+    int4 *yt = (int4 *)(xt + AVD_T);                               // y taps of this band's thumbnail rows
+    const uint32_t bar_full = smem_u32(smem), bar_empty = bar_full + 8 * NRS;
+    const int nwarps_c = cons >> 5;
 
     if (tid == 0) {
-        for (int s = 0; s < NSTAGE; s++) mbar_init(bar0 + 8 * s, 1);
+        for (int s = 0; s < NRS; s++) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, nwarps_c); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
-    __syncthreads();
-    auto issue = [&](int c) {
-        int s = c % NSTAGE, r0 = lo + c * CH, nr = min(CH, hi + 1 - r0);
-        mbar_expect_tx(bar0 + 8 * s, (uint32_t)(nr * P.row_bytes));
-        for (int j = 0; j < nr; j++)
-            tma_load_1d(smem_u32(stage + s * stage_bytes + j * P.row_bytes), src + (size_t)(r0 + j) * P.pitch,
-                        (uint32_t)P.row_bytes, bar0 + 8 * s);
-    };
-    if (tid == 0)
-        for (int c = 0; c < min(NSTAGE, nchunks); c++) issue(c);
-
-    const bool active = 16 * tid < W, first = tid == 0, last = 16 * tid + 16 == W;
-    uint32_t Eu[4] = {0, 0, 0, 0}, Ou[4] = {0, 0, 0, 0};            // gray row r-2 (16-bit lanes: even / odd pixels)
-    uint32_t Ec[4] = {0, 0, 0, 0}, Oc[4] = {0, 0, 0, 0};            // gray row r-1
-    uint32_t HEc[4] = {0, 0, 0, 0}, HOc[4] = {0, 0, 0, 0};          // its horizontal neighbour sums
-    LapAcc A = {0, 0, 0, 0};
-    int ty_next = tab->thumb_row_begin[b];
-    const int ty_end = tab->thumb_row_begin[b + 1];
+    const int ty_begin = tab->thumb_row_begin[b], nty = tab->thumb_row_begin[b + 1] - ty_begin;
     const int thumb_2x2 = tab->thumb_2x2;
-    int g0 = lo;                                                    // first row of the current resample group
+    for (int i = tid; i < AVD_T; i += blockDim.x) {
+        LinTap t = tab->lx[i];
+        if (thumb_2x2) { t.i0 = 2 * i; t.i1 = 2 * i + 1; }
+        xt[i] = make_uint2((uint32_t)t.i0 | ((uint32_t)t.i1 << 16), (uint32_t)t.a0 | ((uint32_t)t.a1 << 16));
+    }
+    for (int i = tid; i < nty; i += blockDim.x) {
+        LinTap t = tab->ly[ty_begin + i];
+        if (thumb_2x2) { t.i0 = 2 * (ty_begin + i); t.i1 = t.i0 + 1; }
+        yt[i] = make_int4(t.i0, t.i1, t.a0, t.a1);
+    }
+    __syncthreads();
 
-    for (int c = 0; c < nchunks; c++) {
-        const int s = c % NSTAGE, r0 = lo + c * CH, nr = min(CH, hi + 1 - r0);
-        mbar_wait(bar0 + 8 * s, (uint32_t)((c / NSTAGE) & 1));
-        if (active) {
-            for (int j = 0; j < nr; j++) {
-                const int r = r0 + j;
-                const uint8_t *sp = stage + s * stage_bytes + j * P.row_bytes + 48 * tid;
-                const uint4 q0 = *(const uint4 *)sp, q1 = *(const uint4 *)(sp + 16), q2 = *(const uint4 *)(sp + 32);
-                uint32_t a[16];
-                gray4(q0.x, q0.y, q0.z, a[0], a[1], a[2], a[3]);
-                gray4(q0.w, q1.x, q1.y, a[4], a[5], a[6], a[7]);
-                gray4(q1.z, q1.w, q2.x, a[8], a[9], a[10], a[11]);
-                gray4(q2.y, q2.z, q2.w, a[12], a[13], a[14], a[15]);
-                // neighbour pixels x-1 and x+16 (REFLECT_101 at the frame edges: x=-1 -> 1, x=W -> W-2)
-                uint32_t aL, aR;
-                if (first) aL = a[1];
-                else { uint32_t w = *(const uint32_t *)(sp - 4); aL = __dp2a_hi(C_GR, w, __dp2a_lo(C_0B, w, RND)); }
-                if (last) aR = a[14];
-                else { uint32_t w = *(const uint32_t *)(sp + 48); aR = __dp2a_hi(C_R0, w, __dp2a_lo(C_BG, w, RND)); }
-                uint32_t E[4], O[4], HE[4], HO[4];
-#pragma unroll
-                for (int g = 0; g < 4; g++) {
-                    E[g] = __byte_perm(a[4 * g], a[4 * g + 2], 0x7632);       // (g0, g2) in 16-bit lanes
-                    O[g] = __byte_perm(a[4 * g + 1], a[4 * g + 3], 0x7632);   // (g1, g3)
-                }
-                uint4 gw;
-                gw.x = __byte_perm(E[0], O[0], 0x6240); gw.y = __byte_perm(E[1], O[1], 0x6240);
-                gw.z = __byte_perm(E[2], O[2], 0x6240); gw.w = __byte_perm(E[3], O[3], 0x6240);
-                *(uint4 *)(ring + ((r - lo) % RC) * W + 16 * tid) = gw;
-#pragma unroll
-                for (int g = 0; g < 4; g++) {
-                    // left neighbours of (g0,g2) are (gL,g1); right neighbours of (g1,g3) are (g2,gR)
-                    uint32_t el = g == 0 ? __byte_perm(aL, O[0], 0x5432) : __byte_perm(O[g - 1], O[g], 0x5432);
-                    uint32_t orr = g == 3 ? __byte_perm(E[3], aR, 0x7632) : __byte_perm(E[g], E[g + 1], 0x5432);
-                    HE[g] = el + O[g];
-                    HO[g] = E[g] + orr;
-                }
-                const int cr = r - 1;                                // centre row whose Laplacian is now complete
-                if (cr >= own0 && cr < own1) {
-                    if (cr == 0) {
-#pragma unroll
-                        for (int g = 0; g < 4; g++) lap4(HEc[g], HOc[g], Ec[g], Oc[g], E[g], O[g], E[g], O[g], A);
-                    } else {
-#pragma unroll
-                        for (int g = 0; g < 4; g++) lap4(HEc[g], HOc[g], Ec[g], Oc[g], Eu[g], Ou[g], E[g], O[g], A);
-                    }
-                }
-#pragma unroll
-                for (int g = 0; g < 4; g++) {
-                    Eu[g] = Ec[g]; Ou[g] = Oc[g];
-                    Ec[g] = E[g]; Oc[g] = O[g]; HEc[g] = HE[g]; HOc[g] = HO[g];
-                }
+    if (tid >= cons) {
+        // ================= producer warp =================
+        if (tid == cons) {
+            uint64_t pol_keep, pol_stream;
+            asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol_keep));
+            asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol_stream));
+            const uint8_t *src = P.bgr + (size_t)f * P.fstride + (size_t)lo * P.pitch;
+            for (int i = 0; i < nrows; i++) {
+                const int s = i % NRS;
+                if (i >= NRS) mbar_wait(bar_empty + 8 * s, (uint32_t)(((i / NRS) - 1) & 1));
+                mbar_expect_tx(bar_full + 8 * s, (uint32_t)P.row_bytes);
+                // the first two rows of a band are read again, later, by the band above: keep them in L2
+                tma_load_1d(smem_u32(stage + s * P.row_bytes), src + (size_t)i * P.pitch, (uint32_t)P.row_bytes,
+                            bar_full + 8 * s, (i < 2 && b > 0) ? pol_keep : pol_stream);
             }
         }
-        __syncthreads();                                             // gray rows visible; stage s is free again
-        if (tid == 0 && c + NSTAGE < nchunks) issue(c + NSTAGE);
+        return;
+    }
 
-        const int g1 = r0 + nr;                                      // one past the last row converted so far
-        if (g1 - g0 >= GR || c == nchunks - 1) {
-            // ---- INTER_AREA horizontal pass for the cell rows of this group (one task per (row, dx)) ----
-            const int ar0 = max(g0, cell_lo), ar1 = min(g1 - 1, cell_hi);
-            for (int id = tid; id < (ar1 - ar0 + 1) * 32; id += nt) {
-                const int row = ar0 + (id >> 5), dx = id & 31;
-                const uint8_t *gr = ring + ((row - lo) % RC) * W;
-                float out;
-                if (area_int) {
-                    const int isx = tab->isx;
-                    unsigned sum = 0;
-                    if (P.area_aligned) {
-                        const uint32_t *wp = (const uint32_t *)(gr + dx * isx);
-                        for (int k = 0; k < (isx >> 2); k++) sum = __dp4a(wp[k], 0x01010101u, sum);
-                    } else {
-                        for (int k = 0; k < isx; k++) sum += gr[dx * isx + k];
-                    }
-                    out = __int_as_float(sum);
-                } else if (P.area_aligned) {
-                    const int cw = W >> 5;
-                    const float alpha = tab->ax[0].am, nb = -8388608.0f * alpha;
-                    const uint32_t *wp = (const uint32_t *)(gr + dx * cw);
-                    float buf = 0.f;
-                    for (int k = 0; k < (cw >> 2); k++) {
-                        uint32_t w = wp[k];
-                        buf = __fadd_rn(buf, mulbyte(w, 0x7650, alpha, nb));
-                        buf = __fadd_rn(buf, mulbyte(w, 0x7651, alpha, nb));
-                        buf = __fadd_rn(buf, mulbyte(w, 0x7652, alpha, nb));
-                        buf = __fadd_rn(buf, mulbyte(w, 0x7653, alpha, nb));
-                    }
-                    out = buf;
+    // ================= consumer warps =================
+    const bool active = 16 * tid < W, first = tid == 0, last = 16 * tid + 16 == W;
+    Band B;
+    B.own0 = own0; B.own1 = own1; B.lo = lo; B.hi = hi; B.H = H; B.W = W; B.cons = cons;
+    B.bar_full = bar_full; B.bar_empty = bar_empty; B.stage = stage; B.ring = ring; B.row_bytes = P.row_bytes;
+    RowSet A0, A1, B0, B1;
+#pragma unroll
+    for (int g = 0; g < 4; g++) {
+        A0.E[g] = A0.O[g] = A0.BE[g] = A0.BO[g] = 0; A1.E[g] = A1.O[g] = A1.BE[g] = A1.BO[g] = 0;
+        B0.E[g] = B0.O[g] = B0.BE[g] = B0.BO[g] = 0; B1.E[g] = B1.O[g] = B1.BE[g] = B1.BO[g] = 0;
+    }
+    LapAcc A = {0, 0, 0, 0};
+    const AreaCell cy = tab->ay[b];
+    const int cell_lo = cy.has_head ? cy.s1 - 1 : cy.s1, cell_hi = cy.has_tail ? cy.s2 : cy.s2 - 1;
+    const int area_int = tab->area_int, isx = tab->isx;
+    const int cw = W >> 5;
+    const float alpha = tab->ax[0].am, nbias = -8388608.0f * alpha;
+    int jty = 0;                                   // next thumbnail row of this band
+    int gslot = 0;                                 // ring slot of the first row of the current group
+
+    for (int i = 0; i < nrows; i += GR) {
+        const int g0 = lo + i, gn = min(GR, nrows - i);
+        // ---- two row pairs: BGR -> gray ring + Laplacian statistics ----
+        {
+            int sl0 = gslot, sl1 = gslot + 1; if (sl1 >= RC) sl1 -= RC;
+            pair_step(B, i, g0, gn > 1, sl0, sl1, tid, active, first, last, B0, B1, A0, A1, A);
+        }
+        if (gn > 2) {
+            int sl0 = gslot + 2; if (sl0 >= RC) sl0 -= RC;
+            int sl1 = gslot + 3; if (sl1 >= RC) sl1 -= RC;
+            pair_step(B, i + 2, g0 + 2, gn > 3, sl0, sl1, tid, active, first, last, A0, A1, B0, B1, A);
+        } else {
+            // the band ended on an odd pair: keep the register roles consistent (nothing follows)
+        }
+        consumer_sync(cons);                       // the group's gray rows are visible to every consumer
+        const int g1 = g0 + gn;
+
+        // ---- INTER_AREA horizontal pass for the cell rows of this group: one task per (row, dx) ----
+        const int ar0 = max(g0, cell_lo), ar1 = min(g1 - 1, cell_hi);
+        for (int id = tid; id < (ar1 - ar0 + 1) * 32; id += cons) {
+            const int row = ar0 + (id >> 5), dx = id & 31;
+            int sl = gslot + (row - g0); if (sl >= RC) sl -= RC;
+            const uint8_t *gr = ring + sl * W;
+            float out;
+            if (area_int) {
+                unsigned sum = 0;
+                if (P.area_aligned) {
+                    const uint32_t *wp = (const uint32_t *)(gr + dx * isx);
+                    for (int k = 0; k < (isx >> 2); k++) sum = __dp4a(wp[k], 0x01010101u, sum);
                 } else {
-                    const AreaCell cx = tab->ax[dx];
-                    float buf = 0.f;
-                    if (cx.has_head) buf = __fadd_rn(buf, __fmul_rn((float)gr[cx.s1 - 1], cx.ah));
-                    for (int k = cx.s1; k < cx.s2; k++) buf = __fadd_rn(buf, __fmul_rn((float)gr[k], cx.am));
-                    if (cx.has_tail) buf = __fadd_rn(buf, __fmul_rn((float)gr[cx.s2], cx.at));
-                    out = buf;
+                    for (int k = 0; k < isx; k++) sum += gr[dx * isx + k];
                 }
-                rowbuf[(row - cell_lo) * 32 + dx] = out;
+                out = __int_as_float(sum);
+            } else if (P.area_aligned) {
+                const uint32_t *wp = (const uint32_t *)(gr + dx * cw);
+                float buf = 0.f;
+                for (int k = 0; k < (cw >> 2); k++) {
+                    uint32_t w = wp[k];
+                    buf = __fadd_rn(buf, mulbyte(w, 0x7650, alpha, nbias));
+                    buf = __fadd_rn(buf, mulbyte(w, 0x7651, alpha, nbias));
+                    buf = __fadd_rn(buf, mulbyte(w, 0x7652, alpha, nbias));
+                    buf = __fadd_rn(buf, mulbyte(w, 0x7653, alpha, nbias));
+                }
+                out = buf;
+            } else {
+                const AreaCell cx = tab->ax[dx];
+                float buf = 0.f;
+                if (cx.has_head) buf = __fadd_rn(buf, __fmul_rn((float)gr[cx.s1 - 1], cx.ah));
+                for (int k = cx.s1; k < cx.s2; k++) buf = __fadd_rn(buf, __fmul_rn((float)gr[k], cx.am));
+                if (cx.has_tail) buf = __fadd_rn(buf, __fmul_rn((float)gr[cx.s2], cx.at));
+                out = buf;
             }
-            // ---- thumbnail rows whose lower tap row is now available ----
-            int tcount = 0;
-            while (ty_next + tcount < ty_end && (thumb_2x2 ? 2 * (ty_next + tcount) + 1 : tab->ly[ty_next + tcount].i1) < g1) tcount++;
-            for (int id = tid; id < tcount * AVD_T; id += nt) {
-                const int ty = ty_next + id / AVD_T, tx = id % AVD_T;
+            rowbuf[(row - cell_lo) * 32 + dx] = out;
+        }
+        // ---- thumbnail rows whose lower tap row is now in the ring ----
+        while (jty < nty) {
+            const int4 vy = yt[jty];
+            if (vy.y >= g1) break;
+            int sa = gslot + (vy.x - g0); if (sa < 0) sa += RC; if (sa >= RC) sa -= RC;
+            int sb = gslot + (vy.y - g0); if (sb < 0) sb += RC; if (sb >= RC) sb -= RC;
+            const uint8_t *p0 = ring + sa * W, *p1 = ring + sb * W;
+            uint8_t *dst = P.thumbs + ((size_t)f * AVD_T + (ty_begin + jty)) * AVD_T;
+            for (int tx = tid; tx < AVD_T; tx += cons) {
+                const uint2 vx = xt[tx];
+                const int x0 = vx.x & 0xffff, x1 = vx.x >> 16;
                 uint8_t o;
                 if (thumb_2x2) {
-                    const uint8_t *p0 = ring + ((2 * ty - lo) % RC) * W + 2 * tx, *p1 = ring + ((2 * ty + 1 - lo) % RC) * W + 2 * tx;
-                    o = (uint8_t)((p0[0] + p0[1] + p1[0] + p1[1] + 2) >> 2);
+                    o = (uint8_t)((p0[x0] + p0[x1] + p1[x0] + p1[x1] + 2) >> 2);
                 } else {
-                    const LinTap vx = tab->lx[tx], vy = tab->ly[ty];
-                    const uint8_t *p0 = ring + ((vy.i0 - lo) % RC) * W, *p1 = ring + ((vy.i1 - lo) % RC) * W;
-                    int S0 = p0[vx.i0] * vx.a0 + p0[vx.i1] * vx.a1;
-                    int S1 = p1[vx.i0] * vx.a0 + p1[vx.i1] * vx.a1;
-                    o = (uint8_t)((((vy.a0 * (S0 >> 4)) >> 16) + ((vy.a1 * (S1 >> 4)) >> 16) + 2) >> 2);
+                    const int a0 = vx.y & 0xffff, a1 = vx.y >> 16;
+                    int S0 = p0[x0] * a0 + p0[x1] * a1;
+                    int S1 = p1[x0] * a0 + p1[x1] * a1;
+                    o = (uint8_t)((((vy.z * (S0 >> 4)) >> 16) + ((vy.w * (S1 >> 4)) >> 16) + 2) >> 2);
                 }
-                P.thumbs[((size_t)f * AVD_T + ty) * AVD_T + tx] = o;
+                dst[tx] = o;
             }
-            ty_next += tcount;
-            g0 = g1;
+            jty++;
         }
-    }
-    // bottom frame edge: Laplacian of row H-1 with REFLECT_101 (row H -> H-2)
-    if (active && own1 == H) {
-#pragma unroll
-        for (int g = 0; g < 4; g++) lap4(HEc[g], HOc[g], Ec[g], Oc[g], Eu[g], Ou[g], Eu[g], Ou[g], A);
+        gslot += gn; if (gslot >= RC) gslot -= RC;
     }
 
     // ---- Laplacian sums: warp shuffle -> shared -> one 64-bit atomic pair per CTA ----
@@ -281,10 +355,9 @@ __global__ void __launch_bounds__(256) k1_fused_kernel(K1Params P)
     for (int o = 16; o; o >>= 1) { s1 += __shfl_down_sync(0xffffffffu, s1, o); sq += __shfl_down_sync(0xffffffffu, sq, o); }
     __shared__ unsigned long long red[2][32];
     if ((tid & 31) == 0) { red[0][tid >> 5] = s1; red[1][tid >> 5] = sq; }
-    __syncthreads();                                                 // also orders rowbuf for the vertical pass
+    consumer_sync(cons);                           // also orders rowbuf for the vertical pass
     if (tid < 32) {
-        const int nw = (nt + 31) >> 5;
-        s1 = tid < nw ? red[0][tid] : 0; sq = tid < nw ? red[1][tid] : 0;
+        s1 = tid < nwarps_c ? red[0][tid] : 0; sq = tid < nwarps_c ? red[1][tid] : 0;
         for (int o = 16; o; o >>= 1) { s1 += __shfl_down_sync(0xffffffffu, s1, o); sq += __shfl_down_sync(0xffffffffu, sq, o); }
         if (tid == 0) {
             const long long npx = (long long)(own1 - own0) * W;
@@ -312,9 +385,16 @@ __global__ void __launch_bounds__(256) k1_fused_kernel(K1Params P)
 
 }  // namespace
 
+static size_t k1_smem_bytes(int W, int max_cell_rows)
+{
+    return 128 + (size_t)NRS * 3 * W + (size_t)RC * W + (size_t)max_cell_rows * 32 * sizeof(float) + AVD_T * sizeof(uint2) +
+           MAX_TY * sizeof(int4);
+}
+
 bool k1_fused_supported(int H, int W, size_t pitch, size_t fstride, const void *base)
 {
-    return W % 16 == 0 && W <= 4096 && pitch % 16 == 0 && fstride % 16 == 0 && ((uintptr_t)base % 16) == 0 && H >= 32;
+    return W % 16 == 0 && W <= 4096 && pitch % 16 == 0 && fstride % 16 == 0 && ((uintptr_t)base % 16) == 0 && H >= 32 &&
+           k1_smem_bytes(W, H / 32 + 3) <= 227 * 1024;
 }
 
 int k1_fused(avd_ctx *ctx, const uint8_t *d_bgr, int n, int H, int W, size_t pitch, size_t fstride,
@@ -330,21 +410,26 @@ int k1_fused(avd_ctx *ctx, const uint8_t *d_bgr, int n, int H, int W, size_t pit
         const AreaCell &c = htab->ay[b];
         int rows = (c.has_tail ? c.s2 : c.s2 - 1) - (c.has_head ? c.s1 - 1 : c.s1) + 1;
         if (rows > max_cell_rows) max_cell_rows = rows;
+        if (htab->thumb_row_begin[b + 1] - htab->thumb_row_begin[b] > MAX_TY) { ctx->err = "fused K1: thumbnail rows per band"; return AVD_ERR_ARG; }
     }
-    size_t smem = 128 + (size_t)NSTAGE * CH * 3 * W + (size_t)RC * W + (size_t)max_cell_rows * 32 * sizeof(float);
+    P.max_cell_rows = max_cell_rows;
+    size_t smem = k1_smem_bytes(W, max_cell_rows);
     if (smem > 227 * 1024) { ctx->err = "fused K1: frame too wide for shared memory"; return AVD_ERR_ARG; }
-    static size_t smem_set = 0;
-    if (smem > smem_set) {
-        AVD_CUDA(ctx, cudaFuncSetAttribute(k1_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        smem_set = smem;
+    int threads = ((W / 16) + 31) / 32 * 32 + 32;                    // consumers + one producer warp
+    const bool narrow = threads <= 160;                              // <= 2048 px wide: 4 CTAs / SM, 102 registers
+    static size_t smem_set[2] = {0, 0};
+    if (smem > smem_set[narrow]) {
+        if (narrow) AVD_CUDA(ctx, cudaFuncSetAttribute(k1_fused_kernel<160, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        else AVD_CUDA(ctx, cudaFuncSetAttribute(k1_fused_kernel<288, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        smem_set[narrow] = smem;
     }
-    int threads = ((W / 16) + 31) / 32 * 32;
     for (int f0 = 0; f0 < n; f0 += 65535) {                          // grid.y limit
         int nb = n - f0 < 65535 ? n - f0 : 65535;
         K1Params Q = P;
         Q.bgr = d_bgr + (size_t)f0 * fstride; Q.rec = d_rec + f0;
         Q.thumbs = d_thumbs + (size_t)f0 * AVD_T * AVD_T; Q.area32 = d_area32 + (size_t)f0 * 1024;
-        AVD_LAUNCH(ctx, "k1_fused", st, k1_fused_kernel<<<dim3(AVD_D, nb), threads, smem, st>>>(Q));
+        if (narrow) AVD_LAUNCH(ctx, "k1_fused", st, (k1_fused_kernel<160, 4><<<dim3(AVD_D, nb), threads, smem, st>>>(Q)));
+        else AVD_LAUNCH(ctx, "k1_fused", st, (k1_fused_kernel<288, 2><<<dim3(AVD_D, nb), threads, smem, st>>>(Q)));
     }
     return AVD_OK;
 }
