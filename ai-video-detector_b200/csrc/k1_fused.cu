@@ -63,11 +63,11 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
         "{\n"
         ".reg .pred P1;\n"
         "LAB_WAIT:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1, %2;\n"
         "@P1 bra DONE;\n"
         "bra LAB_WAIT;\n"
         "DONE:\n"
-        "}" ::"r"(bar), "r"(parity) : "memory");
+        "}" ::"r"(bar), "r"(parity), "r"(20000u) : "memory");   // suspend-time hint: sleep instead of spinning
 }
 __device__ __forceinline__ void consumer_sync(int n) { asm volatile("bar.sync 1, %0;" ::"r"(n) : "memory"); }
 
@@ -91,14 +91,25 @@ struct LapAcc { uint32_t s, ll, hl, hh; };
 struct RowSet { uint32_t E[4], O[4], BE[4], BO[4]; };
 
 // biased Laplacian (L+1020 in [0,2040] per 16-bit lane) of the centre row and its statistics
-__device__ __forceinline__ void lap_row(const RowSet &c, const RowSet &u, const RowSet &d, LapAcc &A)
+//
+// Only the sum of squares is accumulated per pixel.  The plain sum telescopes under REFLECT_101:
+//   sum L = sum_x (g[1][x] + g[H-2][x] - g[0][x] - g[H-1][x]) + sum_y (g[y][1] + g[y][W-2] - g[y][0] - g[y][W-1])
+// so it only needs the first/last two rows (4 rows per frame) and the first/last two pixels of every row.
+__device__ __forceinline__ void lap_row(const RowSet &c, const RowSet &u, const RowSet &d, LapAcc &A, int cr, int H,
+                                        bool first, bool last)
 {
+    if (first) A.s += (c.O[0] & 0xffffu) - (c.E[0] & 0xffffu);        // + g[y][1] - g[y][0]
+    if (last) A.s += (c.E[3] >> 16) - (c.O[3] >> 16);                 // + g[y][W-2] - g[y][W-1]
+    if (cr <= 1 || cr >= H - 2) {                                     // warp-uniform, 4 rows per frame
+        uint32_t t = 0;
+#pragma unroll
+        for (int g = 0; g < 4; g++) { t = __dp2a_lo(c.E[g], 0x0101u, t); t = __dp2a_lo(c.O[g], 0x0101u, t); }
+        A.s += (cr == 1 || cr == H - 2) ? t : 0u - t;
+    }
 #pragma unroll
     for (int g = 0; g < 4; g++) {
         uint32_t le = c.BE[g] + u.E[g] + d.E[g];
         uint32_t lo = c.BO[g] + u.O[g] + d.O[g];
-        A.s = __dp2a_lo(le, 0x0101u, A.s);
-        A.s = __dp2a_lo(lo, 0x0101u, A.s);
         uint32_t pl = __byte_perm(le, lo, 0x6420), ph = __byte_perm(le, lo, 0x7531);
         A.ll = __dp4a(pl, pl, A.ll);
         A.hl = __dp4a(ph, pl, A.hl);
@@ -135,8 +146,9 @@ __device__ __forceinline__ void load_row(const uint8_t *sp, uint8_t *gdst, bool 
         // left neighbours of (g0,g2) are (gL,g1); right neighbours of (g1,g3) are (g2,gR)
         uint32_t el = g == 0 ? __byte_perm(aL, R.O[0], 0x5432) : __byte_perm(R.O[g - 1], R.O[g], 0x5432);
         uint32_t orr = g == 3 ? __byte_perm(R.E[3], aR, 0x7632) : __byte_perm(R.E[g], R.E[g + 1], 0x5432);
-        R.BE[g] = el + R.O[g] + KBIAS - 4u * R.E[g];
-        R.BO[g] = R.E[g] + orr + KBIAS - 4u * R.O[g];
+        const uint32_t me = KBIAS - 4u * R.E[g], mo = KBIAS - 4u * R.O[g];   // one IMAD each, then one IADD3
+        R.BE[g] = el + R.O[g] + me;
+        R.BO[g] = R.E[g] + orr + mo;
     }
 }
 
@@ -178,15 +190,15 @@ __device__ __forceinline__ void pair_step(const Band &B, int i0, int r0, bool ha
     }
     if (!active) return;
     const int cr = r0 - 1;                       // row r0-1 is now complete (down neighbour = c0)
-    if (cr >= B.own0 && cr < B.own1) lap_row(p1, p0, c0, A);
+    if (cr >= B.own0 && cr < B.own1) lap_row(p1, p0, c0, A, cr, B.H, first, last);
     if (have1) {
         if (r0 >= B.own0 && r0 < B.own1) {
-            if (r0 == 0) lap_row(c0, c1, c1, A);  // top frame edge: row -1 reflects to row 1
-            else lap_row(c0, p1, c1, A);
+            if (r0 == 0) lap_row(c0, c1, c1, A, r0, B.H, first, last);  // top frame edge: row -1 reflects to row 1
+            else lap_row(c0, p1, c1, A, r0, B.H, first, last);
         }
-        if (r0 + 1 == B.H - 1 && r0 + 1 < B.own1) lap_row(c1, c0, c0, A);   // bottom frame edge: row H reflects to H-2
+        if (r0 + 1 == B.H - 1 && r0 + 1 < B.own1) lap_row(c1, c0, c0, A, r0 + 1, B.H, first, last);   // bottom frame edge: row H reflects to H-2
     } else if (r0 == B.H - 1 && r0 < B.own1) {
-        lap_row(c0, p1, p1, A);
+        lap_row(c0, p1, p1, A, r0, B.H, first, last);
     }
 }
 
@@ -351,7 +363,7 @@ __global__ void __launch_bounds__(MAXT, MINB) k1_fused_kernel(K1Params P)
     }
 
     // ---- Laplacian sums: warp shuffle -> shared -> one 64-bit atomic pair per CTA ----
-    unsigned long long s1 = A.s, sq = (unsigned long long)A.ll + 512ull * A.hl + 65536ull * A.hh;
+    unsigned long long s1 = (unsigned long long)(long long)(int)A.s, sq = (unsigned long long)A.ll + 512ull * A.hl + 65536ull * A.hh;
     for (int o = 16; o; o >>= 1) { s1 += __shfl_down_sync(0xffffffffu, s1, o); sq += __shfl_down_sync(0xffffffffu, sq, o); }
     __shared__ unsigned long long red[2][32];
     if ((tid & 31) == 0) { red[0][tid >> 5] = s1; red[1][tid >> 5] = sq; }
@@ -361,8 +373,8 @@ __global__ void __launch_bounds__(MAXT, MINB) k1_fused_kernel(K1Params P)
         for (int o = 16; o; o >>= 1) { s1 += __shfl_down_sync(0xffffffffu, s1, o); sq += __shfl_down_sync(0xffffffffu, sq, o); }
         if (tid == 0) {
             const long long npx = (long long)(own1 - own0) * W;
-            const long long sumL = (long long)s1 - 1020ll * npx;
-            const long long sumL2 = (long long)sq - 2040ll * (long long)s1 + 1040400ll * npx;
+            const long long sumL = (long long)s1;                                   // telescoped border sums
+            const long long sumL2 = (long long)sq - 2040ll * sumL - 1040400ll * npx;       // sq = sum (L+1020)^2
             atomicAdd((unsigned long long *)&P.rec[f].lap_sum, (unsigned long long)sumL);
             atomicAdd((unsigned long long *)&P.rec[f].lap_sumsq, (unsigned long long)sumL2);
         }
