@@ -63,11 +63,24 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
         "{\n"
         ".reg .pred P1;\n"
         "LAB_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+        "@P1 bra DONE;\n"
+        "bra LAB_WAIT;\n"
+        "DONE:\n"
+        "}" ::"r"(bar), "r"(parity) : "memory");
+}
+// producer-side wait: it waits most of the time, so give the scheduler a long suspend-time hint
+__device__ __forceinline__ void mbar_wait_sleep(uint32_t bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "LAB_WAIT:\n"
         "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1, %2;\n"
         "@P1 bra DONE;\n"
         "bra LAB_WAIT;\n"
         "DONE:\n"
-        "}" ::"r"(bar), "r"(parity), "r"(20000u) : "memory");   // suspend-time hint: sleep instead of spinning
+        "}" ::"r"(bar), "r"(parity), "r"(100000u) : "memory");
 }
 __device__ __forceinline__ void consumer_sync(int n) { asm volatile("bar.sync 1, %0;" ::"r"(n) : "memory"); }
 
@@ -251,7 +264,7 @@ __global__ void __launch_bounds__(MAXT, MINB) k1_fused_kernel(K1Params P)
             const uint8_t *src = P.bgr + (size_t)f * P.fstride + (size_t)lo * P.pitch;
             for (int i = 0; i < nrows; i++) {
                 const int s = i % NRS;
-                if (i >= NRS) mbar_wait(bar_empty + 8 * s, (uint32_t)(((i / NRS) - 1) & 1));
+                if (i >= NRS) mbar_wait_sleep(bar_empty + 8 * s, (uint32_t)(((i / NRS) - 1) & 1));
                 mbar_expect_tx(bar_full + 8 * s, (uint32_t)P.row_bytes);
                 // the first two rows of a band are read again, later, by the band above: keep them in L2
                 tma_load_1d(smem_u32(stage + s * P.row_bytes), src + (size_t)i * P.pitch, (uint32_t)P.row_bytes,

@@ -250,46 +250,104 @@ __global__ void __launch_bounds__(256) update_matrices_kernel(const float *__res
 constexpr int BS_TW = 32, BS_TH = 32, BS_M = 7, BS_CW = BS_TW + 2 * BS_M;   // 46 columns incl. halo
 constexpr int BS_PITCH = BS_CW + 1;
 
-__global__ void __launch_bounds__(256) blur_solve_kernel(const float *__restrict__ Mall, float *__restrict__ flow, int k)
+// Tile 32x32 outputs.  (0) the M tile with its 7-pixel replicated halo goes to shared memory with fully
+// parallel coalesced loads; (1) vertical 15-row sliding sums, one thread per (channel, column), float64;
+// (2) horizontal 15-column sliding sums in place, one thread per (channel, row); (3) the 2x2 solve.
+// Sliding windows cost 2 adds per (pixel, channel, axis) instead of 15; float64 sums of <=225 float32
+// values are exact to ~1e-16, so the order of summation does not matter (the library uses running sums too).
+// STATS: the last iteration of the finest level also emits per-tile sums of |flow| and |flow|^2.
+constexpr int BS_TILE_F = 5 * BS_CW * BS_PITCH;            // floats of the staged M tile
+constexpr int BS_TILE_D = 5 * BS_TH * BS_PITCH;            // doubles of the sliding sums
+
+template <bool STATS>
+__global__ void __launch_bounds__(256) blur_solve_kernel(const float *__restrict__ Mall, float *__restrict__ flow, int k,
+                                                         double *__restrict__ tile_stats)
 {
     const int s = lvl_size(k);
-    extern __shared__ double vs[];      // [5][BS_TH][BS_PITCH]
-    int x0 = blockIdx.x * BS_TW, y0 = blockIdx.y * BS_TH, p = blockIdx.z;
-    size_t plane = (size_t)s * s;
+    extern __shared__ double vs[];                         // [5][BS_TH][BS_PITCH] doubles, then the float tile
+    float *mt = (float *)(vs + BS_TILE_D);                 // [5][BS_CW rows][BS_PITCH]
+    const int x0 = blockIdx.x * BS_TW, y0 = blockIdx.y * BS_TH, p = blockIdx.z;
+    const size_t plane = (size_t)s * s;
     const float *M = Mall + (size_t)p * 5 * T * T;
-    int tid = threadIdx.y * 32 + threadIdx.x;
+    const int tid = threadIdx.y * 32 + threadIdx.x;
+    for (int idx = tid; idx < 5 * BS_CW * BS_CW; idx += 256) {
+        int c = idx / (BS_CW * BS_CW), rem = idx - c * (BS_CW * BS_CW), row = rem / BS_CW, col = rem - row * BS_CW;
+        int gy = clampi(y0 + row - BS_M, 0, s - 1), gx = clampi(x0 + col - BS_M, 0, s - 1);
+        mt[(c * BS_CW + row) * BS_PITCH + col] = M[c * plane + (size_t)gy * s + gx];
+    }
+    __syncthreads();
     if (tid < 5 * BS_CW) {
-        int c = tid / BS_CW, col = tid % BS_CW;
-        int gx = clampi(x0 + col - BS_M, 0, s - 1);
-        const float *Mc = M + c * plane + gx;
+        const int c = tid / BS_CW, col = tid - c * BS_CW;
+        const float *m = mt + c * BS_CW * BS_PITCH + col;
         double run = 0;
-        for (int j = -BS_M; j <= BS_M; j++) run += (double)Mc[(size_t)clampi(y0 + j, 0, s - 1) * s];
+#pragma unroll
+        for (int j = 0; j < 15; j++) run += (double)m[j * BS_PITCH];
+#pragma unroll 4
         for (int r = 0; r < BS_TH; r++) {
             vs[(c * BS_TH + r) * BS_PITCH + col] = run;
-            run += (double)Mc[(size_t)clampi(y0 + r + BS_M + 1, 0, s - 1) * s] - (double)Mc[(size_t)clampi(y0 + r - BS_M, 0, s - 1) * s];
+            if (r + 15 < BS_CW) run += (double)m[(r + 15) * BS_PITCH] - (double)m[r * BS_PITCH];
         }
     }
     __syncthreads();
-    int x = x0 + threadIdx.x;
-    if (x >= s) return;
+    if (tid < 5 * BS_TH) {
+        double *v = vs + tid * BS_PITCH;                   // tid = c*BS_TH + row
+        double run = 0;
+#pragma unroll
+        for (int j = 0; j < 15; j++) run += v[j];
+#pragma unroll 4
+        for (int x = 0; x < BS_TW; x++) {
+            double old = v[x], nxt = x + 15 < BS_CW ? v[x + 15] : 0.0;
+            v[x] = run;
+            run += nxt - old;
+        }
+    }
+    __syncthreads();
+    const int x = x0 + threadIdx.x;
     const double scale = 1.0 / 225.0;
+    double sm = 0, sq = 0;
     for (int ry = threadIdx.y; ry < BS_TH; ry += 8) {
-        int y = y0 + ry;
-        if (y >= s) break;
+        const int y = y0 + ry;
+        if (x >= s || y >= s) continue;
         double a[5];
 #pragma unroll
-        for (int c = 0; c < 5; c++) {
-            const double *row = vs + (c * BS_TH + ry) * BS_PITCH + threadIdx.x;
-            double t = 0;
-#pragma unroll
-            for (int j = 0; j < 15; j++) t += row[j];
-            a[c] = t * scale;
-        }
+        for (int c = 0; c < 5; c++) a[c] = vs[(c * BS_TH + ry) * BS_PITCH + threadIdx.x] * scale;
         double idet = 1.0 / (a[0] * a[2] - a[1] * a[1] + 1e-3);
         size_t o = (size_t)y * s + x;
-        flow[(size_t)p * 2 * plane + o] = (float)((a[0] * a[4] - a[1] * a[3]) * idet);
-        flow[(size_t)p * 2 * plane + plane + o] = (float)((a[2] * a[3] - a[1] * a[4]) * idet);
+        float fx = (float)((a[0] * a[4] - a[1] * a[3]) * idet), fy = (float)((a[2] * a[3] - a[1] * a[4]) * idet);
+        flow[(size_t)p * 2 * plane + o] = fx;
+        flow[(size_t)p * 2 * plane + plane + o] = fy;
+        if (STATS) {
+            double mag = (double)sqrtf(fx * fx + fy * fy);  // float32 magnitude like np.sqrt(fx**2+fy**2)
+            sm += mag; sq += mag * mag;
+        }
     }
+    if (STATS) {
+        // deterministic: fixed-order block reduction, one partial per tile, summed in tile order afterwards
+        for (int o = 16; o; o >>= 1) { sm += __shfl_down_sync(0xffffffffu, sm, o); sq += __shfl_down_sync(0xffffffffu, sq, o); }
+        __syncthreads();
+        if (threadIdx.x == 0) { vs[threadIdx.y] = sm; vs[8 + threadIdx.y] = sq; }
+        __syncthreads();
+        if (tid == 0) {
+            double a = 0, b = 0;
+            for (int w = 0; w < 8; w++) { a += vs[w]; b += vs[8 + w]; }
+            size_t t = ((size_t)p * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
+            tile_stats[2 * t] = a; tile_stats[2 * t + 1] = b;
+        }
+    }
+}
+
+// mean / variance of |flow| from the per-tile partial sums (fixed order => bit-reproducible)
+__global__ void magstats_finalize_kernel(const double *__restrict__ tile_stats, int tiles, avd_sample_rec *rec, int n_pairs)
+{
+    int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n_pairs) return;
+    double a = 0, b = 0;
+    for (int t = 0; t < tiles; t++) { a += tile_stats[2 * ((size_t)p * tiles + t)]; b += tile_stats[2 * ((size_t)p * tiles + t) + 1]; }
+    const double n = (double)(T * T), mean = a / n;
+    double var = b / n - mean * mean;
+    rec[p].flow_mean = (float)mean;
+    rec[p].flow_var = (float)(var > 0 ? var : 0.0);
+    rec[p].flags |= AVD_REC_HAS_FLOW;
 }
 
 // ---- magnitude statistics -----------------------------------------------------------------------------
@@ -371,10 +429,11 @@ FlowConst make_consts()
 }  // namespace
 
 // Workspace per batch of NI images / NP pairs (floats):
-//   pyr  NI*136000 | R  NI*136000*5 | M  NP*5*320*320 | flowA, flowB  NP*2*320*320 each
+//   pyr  NI*136000 | R  NI*136000*5 | M  NP*5*320*320 | flowA, flowB  NP*2*320*320 each | tile stats NP*100*2 doubles
+constexpr int STAT_TILES = (T / BS_TW) * (T / BS_TH);
 static size_t k2_ws_bytes(int ni, int np)
 {
-    return sizeof(float) * ((size_t)ni * PYR_PX * 6 + (size_t)np * T * T * 9);
+    return sizeof(float) * ((size_t)ni * PYR_PX * 6 + (size_t)np * T * T * 9) + sizeof(double) * 2 * STAT_TILES * (size_t)np;
 }
 
 int k2_flow(avd_ctx *ctx, const uint8_t *d_prev, const uint8_t *d_next, size_t prev_stride, size_t next_stride,
@@ -394,9 +453,10 @@ int k2_flow(avd_ctx *ctx, const uint8_t *d_prev, const uint8_t *d_next, size_t p
     int cap_np = n_pairs < MAXP ? n_pairs : MAXP, cap_ni = shared_chain ? cap_np + 1 : 2 * cap_np;
     if ((rc = avd_ensure(ctx, &ctx->k2_ws, &ctx->k2_ws_cap, k2_ws_bytes(cap_ni, cap_np)))) return rc;
     static bool attr_done = false;
-    size_t bs_smem = sizeof(double) * 5 * BS_TH * BS_PITCH;
+    size_t bs_smem = sizeof(double) * BS_TILE_D + sizeof(float) * BS_TILE_F;
     if (!attr_done) {
-        AVD_CUDA(ctx, cudaFuncSetAttribute(blur_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bs_smem));
+        AVD_CUDA(ctx, cudaFuncSetAttribute(blur_solve_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bs_smem));
+        AVD_CUDA(ctx, cudaFuncSetAttribute(blur_solve_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bs_smem));
         attr_done = true;
     }
     for (int p0 = 0; p0 < n_pairs; p0 += MAXP) {
@@ -404,6 +464,7 @@ int k2_flow(avd_ctx *ctx, const uint8_t *d_prev, const uint8_t *d_next, size_t p
         int ni = shared_chain ? np + 1 : 2 * np;
         float *pyr = (float *)ctx->k2_ws, *R = pyr + (size_t)ni * PYR_PX, *M = R + (size_t)ni * PYR_PX * 5;
         float *flowA = M + (size_t)np * 5 * T * T, *flowB = flowA + (size_t)np * 2 * T * T;
+        double *tile_stats = (double *)(flowB + (size_t)np * 2 * T * T);   // 8-byte aligned: all counts above are even
         ImgSrc src{};
         int mode;
         if (shared_chain) {
@@ -431,7 +492,11 @@ int k2_flow(avd_ctx *ctx, const uint8_t *d_prev, const uint8_t *d_next, size_t p
                 AVD_LAUNCH(ctx, "update_matrices", st, update_matrices_kernel<2><<<gu, bu, 0, st>>>(R, nullptr, prev, M, nullptr, k, mode));
             }
             for (int it = 0; it < 3; it++) {
-                AVD_LAUNCH(ctx, "blur_solve", st, blur_solve_kernel<<<gb, bu, bs_smem, st>>>(M, cur, k));
+                if (k == 0 && it == 2 && d_rec_first) {
+                    AVD_LAUNCH(ctx, "blur_solve", st, blur_solve_kernel<true><<<gb, bu, bs_smem, st>>>(M, cur, k, tile_stats));
+                } else {
+                    AVD_LAUNCH(ctx, "blur_solve", st, blur_solve_kernel<false><<<gb, bu, bs_smem, st>>>(M, cur, k, nullptr));
+                }
                 if (it < 2) {
                     AVD_LAUNCH(ctx, "update_matrices", st, update_matrices_kernel<1><<<gu, bu, 0, st>>>(R, cur, nullptr, M, nullptr, k, mode));
                 }
@@ -440,7 +505,7 @@ int k2_flow(avd_ctx *ctx, const uint8_t *d_prev, const uint8_t *d_next, size_t p
         }
         if (d_rec_first) {
             // chain: pair p0+j -> record of its "next" image
-            AVD_LAUNCH(ctx, "magstats", st, magstats_kernel<<<np, 1024, 0, st>>>(prev, d_rec_first + p0, 1));
+            AVD_LAUNCH(ctx, "magstats", st, magstats_finalize_kernel<<<(np + 127) / 128, 128, 0, st>>>(tile_stats, STAT_TILES, d_rec_first + p0, np));
         }
         if (d_flow_out) {
             size_t total = (size_t)np * T * T;
