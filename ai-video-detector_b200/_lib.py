@@ -8,7 +8,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libavd.so")
+LIB_PATH = os.environ.get("AVD_LIB") or os.path.join(_HERE, "csrc", "libavd.so")   # AVD_LIB: A/B kernel variants
 
 THUMB = 320
 REC_DTYPE = np.dtype([("lap_sum", "<i8"), ("lap_sumsq", "<i8"), ("flow_mean", "<f4"), ("flow_var", "<f4"),

@@ -23,7 +23,20 @@
 
 namespace {
 
-constexpr int NRS = 4;                // single-row TMA stages in flight per CTA
+// build-time tunables (scripts/build_variants.sh builds A/B libraries with -D overrides)
+#ifndef K1_NRS
+#define K1_NRS 4
+#endif
+#ifndef K1_PRODUCER_SLEEP
+#define K1_PRODUCER_SLEEP 1
+#endif
+#ifndef K1_TELESCOPE
+#define K1_TELESCOPE 1
+#endif
+#ifndef K1_MINB
+#define K1_MINB 4
+#endif
+constexpr int NRS = K1_NRS;           // single-row TMA stages in flight per CTA
 constexpr int GR = 4;                 // rows per resample group (two row pairs)
 constexpr int RC = 2 * GR + 1;        // gray ring rows: previous group + carry row + group being written
 constexpr int MAX_TY = 32;            // thumbnail rows one band can own
@@ -111,6 +124,7 @@ struct RowSet { uint32_t E[4], O[4], BE[4], BO[4]; };
 __device__ __forceinline__ void lap_row(const RowSet &c, const RowSet &u, const RowSet &d, LapAcc &A, int cr, int H,
                                         bool first, bool last)
 {
+#if K1_TELESCOPE
     if (first) A.s += (c.O[0] & 0xffffu) - (c.E[0] & 0xffffu);        // + g[y][1] - g[y][0]
     if (last) A.s += (c.E[3] >> 16) - (c.O[3] >> 16);                 // + g[y][W-2] - g[y][W-1]
     if (cr <= 1 || cr >= H - 2) {                                     // warp-uniform, 4 rows per frame
@@ -119,10 +133,15 @@ __device__ __forceinline__ void lap_row(const RowSet &c, const RowSet &u, const 
         for (int g = 0; g < 4; g++) { t = __dp2a_lo(c.E[g], 0x0101u, t); t = __dp2a_lo(c.O[g], 0x0101u, t); }
         A.s += (cr == 1 || cr == H - 2) ? t : 0u - t;
     }
+#endif
 #pragma unroll
     for (int g = 0; g < 4; g++) {
         uint32_t le = c.BE[g] + u.E[g] + d.E[g];
         uint32_t lo = c.BO[g] + u.O[g] + d.O[g];
+#if !K1_TELESCOPE
+        A.s = __dp2a_lo(le, 0x0101u, A.s);
+        A.s = __dp2a_lo(lo, 0x0101u, A.s);
+#endif
         uint32_t pl = __byte_perm(le, lo, 0x6420), ph = __byte_perm(le, lo, 0x7531);
         A.ll = __dp4a(pl, pl, A.ll);
         A.hl = __dp4a(ph, pl, A.hl);
@@ -264,7 +283,11 @@ __global__ void __launch_bounds__(MAXT, MINB) k1_fused_kernel(K1Params P)
             const uint8_t *src = P.bgr + (size_t)f * P.fstride + (size_t)lo * P.pitch;
             for (int i = 0; i < nrows; i++) {
                 const int s = i % NRS;
+#if K1_PRODUCER_SLEEP
                 if (i >= NRS) mbar_wait_sleep(bar_empty + 8 * s, (uint32_t)(((i / NRS) - 1) & 1));
+#else
+                if (i >= NRS) mbar_wait(bar_empty + 8 * s, (uint32_t)(((i / NRS) - 1) & 1));
+#endif
                 mbar_expect_tx(bar_full + 8 * s, (uint32_t)P.row_bytes);
                 // the first two rows of a band are read again, later, by the band above: keep them in L2
                 tma_load_1d(smem_u32(stage + s * P.row_bytes), src + (size_t)i * P.pitch, (uint32_t)P.row_bytes,
@@ -376,7 +399,12 @@ __global__ void __launch_bounds__(MAXT, MINB) k1_fused_kernel(K1Params P)
     }
 
     // ---- Laplacian sums: warp shuffle -> shared -> one 64-bit atomic pair per CTA ----
-    unsigned long long s1 = (unsigned long long)(long long)(int)A.s, sq = (unsigned long long)A.ll + 512ull * A.hl + 65536ull * A.hh;
+#if K1_TELESCOPE
+    unsigned long long s1 = (unsigned long long)(long long)(int)A.s;
+#else
+    unsigned long long s1 = A.s;
+#endif
+    unsigned long long sq = (unsigned long long)A.ll + 512ull * A.hl + 65536ull * A.hh;
     for (int o = 16; o; o >>= 1) { s1 += __shfl_down_sync(0xffffffffu, s1, o); sq += __shfl_down_sync(0xffffffffu, sq, o); }
     __shared__ unsigned long long red[2][32];
     if ((tid & 31) == 0) { red[0][tid >> 5] = s1; red[1][tid >> 5] = sq; }
@@ -386,7 +414,11 @@ __global__ void __launch_bounds__(MAXT, MINB) k1_fused_kernel(K1Params P)
         for (int o = 16; o; o >>= 1) { s1 += __shfl_down_sync(0xffffffffu, s1, o); sq += __shfl_down_sync(0xffffffffu, sq, o); }
         if (tid == 0) {
             const long long npx = (long long)(own1 - own0) * W;
+#if K1_TELESCOPE
             const long long sumL = (long long)s1;                                   // telescoped border sums
+#else
+            const long long sumL = (long long)s1 - 1020ll * npx;                    // s1 = sum (L+1020)
+#endif
             const long long sumL2 = (long long)sq - 2040ll * sumL - 1040400ll * npx;       // sq = sum (L+1020)^2
             atomicAdd((unsigned long long *)&P.rec[f].lap_sum, (unsigned long long)sumL);
             atomicAdd((unsigned long long *)&P.rec[f].lap_sumsq, (unsigned long long)sumL2);
@@ -444,7 +476,7 @@ int k1_fused(avd_ctx *ctx, const uint8_t *d_bgr, int n, int H, int W, size_t pit
     const bool narrow = threads <= 160;                              // <= 2048 px wide: 4 CTAs / SM, 102 registers
     static size_t smem_set[2] = {0, 0};
     if (smem > smem_set[narrow]) {
-        if (narrow) AVD_CUDA(ctx, cudaFuncSetAttribute(k1_fused_kernel<160, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        if (narrow) AVD_CUDA(ctx, cudaFuncSetAttribute(k1_fused_kernel<160, K1_MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         else AVD_CUDA(ctx, cudaFuncSetAttribute(k1_fused_kernel<288, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         smem_set[narrow] = smem;
     }
@@ -453,7 +485,7 @@ int k1_fused(avd_ctx *ctx, const uint8_t *d_bgr, int n, int H, int W, size_t pit
         K1Params Q = P;
         Q.bgr = d_bgr + (size_t)f0 * fstride; Q.rec = d_rec + f0;
         Q.thumbs = d_thumbs + (size_t)f0 * AVD_T * AVD_T; Q.area32 = d_area32 + (size_t)f0 * 1024;
-        if (narrow) AVD_LAUNCH(ctx, "k1_fused", st, (k1_fused_kernel<160, 4><<<dim3(AVD_D, nb), threads, smem, st>>>(Q)));
+        if (narrow) AVD_LAUNCH(ctx, "k1_fused", st, (k1_fused_kernel<160, K1_MINB><<<dim3(AVD_D, nb), threads, smem, st>>>(Q)));
         else AVD_LAUNCH(ctx, "k1_fused", st, (k1_fused_kernel<288, 2><<<dim3(AVD_D, nb), threads, smem, st>>>(Q)));
     }
     return AVD_OK;

@@ -75,36 +75,35 @@ __device__ __forceinline__ void blur_taps(const uint8_t *__restrict__ img, int x
         }
 }
 
+template <int K>
 __global__ void __launch_bounds__(128) pyr_kernel(ImgSrc src, float *__restrict__ pyr)
 {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= PYR_PX) return;
+    constexpr int S = lvl_size(K);
+    int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= S * S) return;
     int img_i = blockIdx.y;
     const uint8_t *img = img_ptr(src, img_i);
-    float *out = pyr + (size_t)img_i * PYR_PX;
-    const float k0[2] = {0.5f, 0.25f};
-    if (i >= lvl_off(0)) {
-        int p = i - lvl_off(0), y = p / 320, x = p % 320;
+    float *out = pyr + (size_t)img_i * PYR_PX + lvl_off(K);
+    const int y = p / S, x = p % S;
+    if (K == 0) {
+        const float k0[2] = {0.5f, 0.25f};
         float o[1][1];
         blur_taps<1, 1, 1>(img, x, y, k0, o);
-        out[i] = o[0][0];
-    } else if (i >= lvl_off(1)) {          // 320 -> 160: exact 2x => 2x2 area mean
-        int p = i - lvl_off(1), y = p / 160, x = p % 160;
+        out[p] = o[0][0];
+    } else if (K == 1) {                   // 320 -> 160: exact 2x => 2x2 area mean
         float o[2][2];
         blur_taps<1, 2, 2>(img, 2 * x, 2 * y, FC.k1, o);
-        out[i] = (((o[0][0] + o[0][1]) + o[1][0]) + o[1][1]) * 0.25f;
-    } else if (i >= lvl_off(2)) {          // 320 -> 80: bilinear at 4x+1.5 (weights .5/.5)
-        int p = i - lvl_off(2), y = p / 80, x = p % 80;
+        out[p] = (((o[0][0] + o[0][1]) + o[1][0]) + o[1][1]) * 0.25f;
+    } else if (K == 2) {                   // 320 -> 80: bilinear at 4x+1.5 (weights .5/.5)
         float o[2][2];
         blur_taps<4, 2, 2>(img, 4 * x + 1, 4 * y + 1, FC.k2, o);
         float r0 = o[0][0] * 0.5f + o[0][1] * 0.5f, r1 = o[1][0] * 0.5f + o[1][1] * 0.5f;
-        out[i] = r0 * 0.5f + r1 * 0.5f;
+        out[p] = r0 * 0.5f + r1 * 0.5f;
     } else {                               // 320 -> 40: bilinear at 8x+3.5
-        int y = i / 40, x = i % 40;
         float o[2][2];
         blur_taps<9, 2, 2>(img, 8 * x + 3, 8 * y + 3, FC.k3, o);
         float r0 = o[0][0] * 0.5f + o[0][1] * 0.5f, r1 = o[1][0] * 0.5f + o[1][1] * 0.5f;
-        out[i] = r0 * 0.5f + r1 * 0.5f;
+        out[p] = r0 * 0.5f + r1 * 0.5f;
     }
 }
 
@@ -270,10 +269,20 @@ __global__ void __launch_bounds__(256) blur_solve_kernel(const float *__restrict
     const size_t plane = (size_t)s * s;
     const float *M = Mall + (size_t)p * 5 * T * T;
     const int tid = threadIdx.y * 32 + threadIdx.x;
-    for (int idx = tid; idx < 5 * BS_CW * BS_CW; idx += 256) {
-        int c = idx / (BS_CW * BS_CW), rem = idx - c * (BS_CW * BS_CW), row = rem / BS_CW, col = rem - row * BS_CW;
-        int gy = clampi(y0 + row - BS_M, 0, s - 1), gx = clampi(x0 + col - BS_M, 0, s - 1);
-        mt[(c * BS_CW + row) * BS_PITCH + col] = M[c * plane + (size_t)gy * s + gx];
+    {   // stage the tile: warp w takes rows w, w+8, ...; lanes take columns lane and lane+32 (no divisions)
+        const int lane = threadIdx.x, w = threadIdx.y;
+        const int gxa = clampi(x0 + lane - BS_M, 0, s - 1), gxb = clampi(x0 + lane + 32 - BS_M, 0, s - 1);
+        const bool hasb = lane + 32 < BS_CW;
+#pragma unroll 2
+        for (int row = w; row < BS_CW; row += 8) {
+            const float *src = M + (size_t)clampi(y0 + row - BS_M, 0, s - 1) * s;
+            float *dst = mt + row * BS_PITCH + lane;
+#pragma unroll
+            for (int c = 0; c < 5; c++) {
+                dst[c * BS_CW * BS_PITCH] = src[c * plane + gxa];
+                if (hasb) dst[c * BS_CW * BS_PITCH + 32] = src[c * plane + gxb];
+            }
+        }
     }
     __syncthreads();
     if (tid < 5 * BS_CW) {
@@ -476,7 +485,10 @@ int k2_flow(avd_ctx *ctx, const uint8_t *d_prev, const uint8_t *d_next, size_t p
             src.mode = 2; src.a = d_prev + (size_t)p0 * prev_stride; src.b = d_next + (size_t)p0 * next_stride;
             src.sa = prev_stride; src.sb = next_stride; mode = 2;
         }
-        AVD_LAUNCH(ctx, "pyr", st, pyr_kernel<<<dim3((PYR_PX + 127) / 128, ni), 128, 0, st>>>(src, pyr));
+        AVD_LAUNCH(ctx, "pyr", st, pyr_kernel<3><<<dim3((40 * 40 + 127) / 128, ni), 128, 0, st>>>(src, pyr));
+        AVD_LAUNCH(ctx, "pyr", st, pyr_kernel<2><<<dim3((80 * 80 + 127) / 128, ni), 128, 0, st>>>(src, pyr));
+        AVD_LAUNCH(ctx, "pyr", st, pyr_kernel<1><<<dim3((160 * 160 + 127) / 128, ni), 128, 0, st>>>(src, pyr));
+        AVD_LAUNCH(ctx, "pyr", st, pyr_kernel<0><<<dim3((320 * 320 + 127) / 128, ni), 128, 0, st>>>(src, pyr));
         for (int k = 3; k >= 0; k--) {
             int s = lvl_size(k);
             AVD_LAUNCH(ctx, "polyexp", st, polyexp_kernel<<<dim3((s + PE_TW - 1) / PE_TW, (s + PE_TH - 1) / PE_TH, ni), dim3(PE_TW, PE_TH), 0, st>>>(pyr, R, k));
