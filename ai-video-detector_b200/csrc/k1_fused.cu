@@ -5,9 +5,11 @@
 //
 // Decomposition: CTA = (frame, band b), band b = the source rows of INTER_AREA destination row b
 // (H/32 rows plus one halo row above and below for the Laplacian / fractional cell taps).
-//   producer warp   one lane streams the band's rows into a ring of single-row shared-memory stages with
-//                   TMA bulk copies (cp.async.bulk -> UBLKCP), full/empty mbarriers per stage
-//   consumer warps  each thread owns a 16-pixel column strip (48 bytes = 3 conflict-free LDS.128) and
+//   TMA ring        the band's rows stream into a ring of single-row shared-memory stages with TMA bulk
+//                   copies (cp.async.bulk -> UBLKCP) completing on per-stage mbarriers; the warp that is
+//                   LAST to finish reading a stage (shared-memory arrival counter) refills it, so nobody
+//                   ever waits for a stage to become free
+//   all warps       each thread owns a 16-pixel column strip (48 bytes = 3 conflict-free LDS.128) and
 //                   marches down the band two rows at a time, keeping the previous rows in registers
 //                   (two alternating register sets, so no register shuffling), writes packed gray to a
 //                   small ring; every 4 rows all consumers meet once (named barrier) and then run the
@@ -31,10 +33,10 @@ namespace {
 #define K1_PRODUCER_SLEEP 1
 #endif
 #ifndef K1_TELESCOPE
-#define K1_TELESCOPE 1
+#define K1_TELESCOPE 0
 #endif
 #ifndef K1_MINB
-#define K1_MINB 4
+#define K1_MINB 5
 #endif
 constexpr int NRS = K1_NRS;           // single-row TMA stages in flight per CTA
 constexpr int GR = 4;                 // rows per resample group (two row pairs)
@@ -197,12 +199,37 @@ __device__ __forceinline__ float mulbyte(uint32_t word, uint32_t sel, float alph
 }
 
 struct Band {
-    int own0, own1, lo, hi, H, W, cons;   // cons = consumer threads
-    uint32_t bar_full, bar_empty;
+    int own0, own1, lo, hi, H, W, nrows, nwarps;
+    uint32_t bar_full, cnt;               // shared addresses: full barriers [NRS], arrival counters [NRS]
     const uint8_t *stage;
     uint8_t *ring;
     int row_bytes;
+    const uint8_t *src;                   // first loaded row of the band in global memory
+    size_t pitch;
+    uint64_t pol_keep, pol_stream;
+    bool keep_first_rows;
 };
+
+__device__ __forceinline__ void issue_row(const Band &B, int i)
+{
+    const int s = i % NRS;
+    mbar_expect_tx(B.bar_full + 8 * s, (uint32_t)B.row_bytes);
+    // the first two rows of a band are read again, later, by the band above: keep them in L2
+    tma_load_1d(smem_u32(B.stage + s * B.row_bytes), B.src + (size_t)i * B.pitch, (uint32_t)B.row_bytes, B.bar_full + 8 * s,
+                (i < 2 && B.keep_first_rows) ? B.pol_keep : B.pol_stream);
+}
+
+// this warp is done reading stage s (row i): the last warp to say so refills the stage with row i+NRS
+__device__ __forceinline__ void release_stage(const Band &B, int i)
+{
+    const int s = i % NRS;
+    uint32_t old;
+    asm volatile("atom.acq_rel.cta.shared::cta.add.u32 %0, [%1], 1;" : "=r"(old) : "r"(B.cnt + 4 * s) : "memory");
+    if (old == (uint32_t)(B.nwarps - 1)) {
+        asm volatile("st.relaxed.cta.shared::cta.u32 [%0], %1;" ::"r"(B.cnt + 4 * s), "r"(0u) : "memory");
+        if (i + NRS < B.nrows) issue_row(B, i + NRS);
+    }
+}
 
 // rows (r0, r0+1) of the band: p0/p1 hold rows r0-2, r0-1; c0/c1 receive rows r0, r0+1
 __device__ __forceinline__ void pair_step(const Band &B, int i0, int r0, bool have1, int slot0, int slot1, int tid, bool active,
@@ -216,9 +243,9 @@ __device__ __forceinline__ void pair_step(const Band &B, int i0, int r0, bool ha
         if (active) load_row(B.stage + s1 * B.row_bytes + 48 * tid, B.ring + slot1 * B.W + 16 * tid, first, last, c1);
     }
     __syncwarp();
-    if ((tid & 31) == 0) {                       // this warp is done with both stages: hand them back to the producer
-        mbar_arrive(B.bar_empty + 8 * s0);
-        if (have1) mbar_arrive(B.bar_empty + 8 * s1);
+    if ((tid & 31) == 0) {                       // this warp is done with both stages
+        release_stage(B, i0);
+        if (have1) release_stage(B, i0 + 1);
     }
     if (!active) return;
     const int cr = r0 - 1;                       // row r0-1 is now complete (down neighbour = c0)
@@ -239,7 +266,7 @@ __global__ void __launch_bounds__(MAXT, MINB) k1_fused_kernel(K1Params P)
 {
     extern __shared__ __align__(128) uint8_t smem[];
     const int tid = threadIdx.x;
-    const int cons = blockDim.x - 32;            // consumer threads; the last warp is the TMA producer
+    const int cons = blockDim.x;                 // every warp is a consumer
     const int b = blockIdx.x, f = blockIdx.y;
     const ShapeTables *__restrict__ tab = P.tab;
     const int H = P.H, W = P.W;
@@ -249,14 +276,17 @@ __global__ void __launch_bounds__(MAXT, MINB) k1_fused_kernel(K1Params P)
     // shared memory carve-up
     uint8_t *stage = smem + 128;                                   // NRS rows of BGR
     uint8_t *ring = stage + NRS * P.row_bytes;                     // RC rows of gray
-    float *rowbuf = (float *)(ring + RC * W);                      // INTER_AREA row partials [cell rows][32]
-    uint2 *xt = (uint2 *)(rowbuf + P.max_cell_rows * 32);          // packed x taps of the thumbnail [320]
+    float *rowbuf = (float *)(ring + RC * W);                      // INTER_AREA row partials, double-buffered [2][GR][32]
+    uint2 *xt = (uint2 *)(rowbuf + 2 * GR * 32);                   // packed x taps of the thumbnail [320]
     int4 *yt = (int4 *)(xt + AVD_T);                               // y taps of this band's thumbnail rows
-    const uint32_t bar_full = smem_u32(smem), bar_empty = bar_full + 8 * NRS;
+    const uint32_t bar_full = smem_u32(smem), cnt = bar_full + 8 * NRS;
     const int nwarps_c = cons >> 5;
 
     if (tid == 0) {
-        for (int s = 0; s < NRS; s++) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, nwarps_c); }
+        for (int s = 0; s < NRS; s++) {
+            mbar_init(bar_full + 8 * s, 1);
+            asm volatile("st.relaxed.cta.shared::cta.u32 [%0], %1;" ::"r"(cnt + 4 * s), "r"(0u) : "memory");
+        }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
@@ -274,34 +304,15 @@ __global__ void __launch_bounds__(MAXT, MINB) k1_fused_kernel(K1Params P)
     }
     __syncthreads();
 
-    if (tid >= cons) {
-        // ================= producer warp =================
-        if (tid == cons) {
-            uint64_t pol_keep, pol_stream;
-            asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol_keep));
-            asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol_stream));
-            const uint8_t *src = P.bgr + (size_t)f * P.fstride + (size_t)lo * P.pitch;
-            for (int i = 0; i < nrows; i++) {
-                const int s = i % NRS;
-#if K1_PRODUCER_SLEEP
-                if (i >= NRS) mbar_wait_sleep(bar_empty + 8 * s, (uint32_t)(((i / NRS) - 1) & 1));
-#else
-                if (i >= NRS) mbar_wait(bar_empty + 8 * s, (uint32_t)(((i / NRS) - 1) & 1));
-#endif
-                mbar_expect_tx(bar_full + 8 * s, (uint32_t)P.row_bytes);
-                // the first two rows of a band are read again, later, by the band above: keep them in L2
-                tma_load_1d(smem_u32(stage + s * P.row_bytes), src + (size_t)i * P.pitch, (uint32_t)P.row_bytes,
-                            bar_full + 8 * s, (i < 2 && b > 0) ? pol_keep : pol_stream);
-            }
-        }
-        return;
-    }
-
-    // ================= consumer warps =================
     const bool active = 16 * tid < W, first = tid == 0, last = 16 * tid + 16 == W;
     Band B;
-    B.own0 = own0; B.own1 = own1; B.lo = lo; B.hi = hi; B.H = H; B.W = W; B.cons = cons;
-    B.bar_full = bar_full; B.bar_empty = bar_empty; B.stage = stage; B.ring = ring; B.row_bytes = P.row_bytes;
+    B.own0 = own0; B.own1 = own1; B.lo = lo; B.hi = hi; B.H = H; B.W = W; B.nrows = nrows; B.nwarps = nwarps_c;
+    B.bar_full = bar_full; B.cnt = cnt; B.stage = stage; B.ring = ring; B.row_bytes = P.row_bytes;
+    B.src = P.bgr + (size_t)f * P.fstride + (size_t)lo * P.pitch; B.pitch = P.pitch; B.keep_first_rows = b > 0;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(B.pol_keep));
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(B.pol_stream));
+    if (tid == 0)
+        for (int i = 0; i < min(NRS, nrows); i++) issue_row(B, i);
     RowSet A0, A1, B0, B1;
 #pragma unroll
     for (int g = 0; g < 4; g++) {
@@ -316,8 +327,22 @@ __global__ void __launch_bounds__(MAXT, MINB) k1_fused_kernel(K1Params P)
     const float alpha = tab->ax[0].am, nbias = -8388608.0f * alpha;
     int jty = 0;                                   // next thumbnail row of this band
     int gslot = 0;                                 // ring slot of the first row of the current group
+    // INTER_AREA vertical pass, folded progressively by thread dx = tid < 32 (sequential over rows, as mandated)
+    float vsum = 0.f;
+    int vtot = 0, pg0 = 0, pgn = 0, gi = 0;
+    auto fold = [&](int fg0, int fgn, const float *buf) {
+        const int r0 = max(fg0, cell_lo), r1 = min(fg0 + fgn - 1, cell_hi);
+        for (int r = r0; r <= r1; r++) {
+            const float v = buf[(r - fg0) * 32 + tid];
+            if (area_int) vtot += __float_as_int(v);
+            else {
+                const float beta = (cy.has_head && r == cell_lo) ? cy.ah : ((cy.has_tail && r == cy.s2) ? cy.at : cy.am);
+                vsum = __fadd_rn(vsum, __fmul_rn(beta, v));
+            }
+        }
+    };
 
-    for (int i = 0; i < nrows; i += GR) {
+    for (int i = 0; i < nrows; i += GR, gi++) {
         const int g0 = lo + i, gn = min(GR, nrows - i);
         // ---- two row pairs: BGR -> gray ring + Laplacian statistics ----
         {
@@ -333,6 +358,9 @@ __global__ void __launch_bounds__(MAXT, MINB) k1_fused_kernel(K1Params P)
         }
         consumer_sync(cons);                       // the group's gray rows are visible to every consumer
         const int g1 = g0 + gn;
+        float *rb = rowbuf + (gi & 1) * GR * 32;
+        if (tid < 32 && pgn) fold(pg0, pgn, rowbuf + ((gi & 1) ^ 1) * GR * 32);   // previous group's partials
+        pg0 = g0; pgn = gn;
 
         // ---- INTER_AREA horizontal pass for the cell rows of this group: one task per (row, dx) ----
         const int ar0 = max(g0, cell_lo), ar1 = min(g1 - 1, cell_hi);
@@ -369,7 +397,7 @@ __global__ void __launch_bounds__(MAXT, MINB) k1_fused_kernel(K1Params P)
                 if (cx.has_tail) buf = __fadd_rn(buf, __fmul_rn((float)gr[cx.s2], cx.at));
                 out = buf;
             }
-            rowbuf[(row - cell_lo) * 32 + dx] = out;
+            rb[(row - g0) * 32 + dx] = out;
         }
         // ---- thumbnail rows whose lower tap row is now in the ring ----
         while (jty < nty) {
@@ -408,7 +436,7 @@ __global__ void __launch_bounds__(MAXT, MINB) k1_fused_kernel(K1Params P)
     for (int o = 16; o; o >>= 1) { s1 += __shfl_down_sync(0xffffffffu, s1, o); sq += __shfl_down_sync(0xffffffffu, sq, o); }
     __shared__ unsigned long long red[2][32];
     if ((tid & 31) == 0) { red[0][tid >> 5] = s1; red[1][tid >> 5] = sq; }
-    consumer_sync(cons);                           // also orders rowbuf for the vertical pass
+    consumer_sync(cons);                           // also orders the last group's row partials
     if (tid < 32) {
         s1 = tid < nwarps_c ? red[0][tid] : 0; sq = tid < nwarps_c ? red[1][tid] : 0;
         for (int o = 16; o; o >>= 1) { s1 += __shfl_down_sync(0xffffffffu, s1, o); sq += __shfl_down_sync(0xffffffffu, sq, o); }
@@ -424,19 +452,8 @@ __global__ void __launch_bounds__(MAXT, MINB) k1_fused_kernel(K1Params P)
             atomicAdd((unsigned long long *)&P.rec[f].lap_sumsq, (unsigned long long)sumL2);
         }
         // ---- INTER_AREA vertical pass: destination row b, column tid ----
-        uint8_t o;
-        if (area_int) {
-            int tot = 0;
-            for (int r = cell_lo; r <= cell_hi; r++) tot += __float_as_int(rowbuf[(r - cell_lo) * 32 + tid]);
-            o = sat_rne(__fmul_rn((float)tot, tab->inv_area));
-        } else {
-            float sum = 0.f;
-            if (cy.has_head) sum = __fadd_rn(sum, __fmul_rn(cy.ah, rowbuf[tid]));
-            for (int r = cy.s1; r < cy.s2; r++) sum = __fadd_rn(sum, __fmul_rn(cy.am, rowbuf[(r - cell_lo) * 32 + tid]));
-            if (cy.has_tail) sum = __fadd_rn(sum, __fmul_rn(cy.at, rowbuf[(cy.s2 - cell_lo) * 32 + tid]));
-            o = sat_rne(sum);
-        }
-        P.area32[(size_t)f * 1024 + b * 32 + tid] = o;
+        if (pgn) fold(pg0, pgn, rowbuf + ((gi & 1) ^ 1) * GR * 32);      // gi was incremented past the last group
+        P.area32[(size_t)f * 1024 + b * 32 + tid] = area_int ? sat_rne(__fmul_rn((float)vtot, tab->inv_area)) : sat_rne(vsum);
     }
 }
 
@@ -444,7 +461,8 @@ __global__ void __launch_bounds__(MAXT, MINB) k1_fused_kernel(K1Params P)
 
 static size_t k1_smem_bytes(int W, int max_cell_rows)
 {
-    return 128 + (size_t)NRS * 3 * W + (size_t)RC * W + (size_t)max_cell_rows * 32 * sizeof(float) + AVD_T * sizeof(uint2) +
+    (void)max_cell_rows;
+    return 128 + (size_t)NRS * 3 * W + (size_t)RC * W + (size_t)2 * GR * 32 * sizeof(float) + AVD_T * sizeof(uint2) +
            MAX_TY * sizeof(int4);
 }
 
@@ -472,12 +490,12 @@ int k1_fused(avd_ctx *ctx, const uint8_t *d_bgr, int n, int H, int W, size_t pit
     P.max_cell_rows = max_cell_rows;
     size_t smem = k1_smem_bytes(W, max_cell_rows);
     if (smem > 227 * 1024) { ctx->err = "fused K1: frame too wide for shared memory"; return AVD_ERR_ARG; }
-    int threads = ((W / 16) + 31) / 32 * 32 + 32;                    // consumers + one producer warp
-    const bool narrow = threads <= 160;                              // <= 2048 px wide: 4 CTAs / SM, 102 registers
+    int threads = ((W / 16) + 31) / 32 * 32;
+    const bool narrow = threads <= 128;                              // <= 2048 px wide: 5 CTAs / SM, <= 102 registers
     static size_t smem_set[2] = {0, 0};
     if (smem > smem_set[narrow]) {
-        if (narrow) AVD_CUDA(ctx, cudaFuncSetAttribute(k1_fused_kernel<160, K1_MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        else AVD_CUDA(ctx, cudaFuncSetAttribute(k1_fused_kernel<288, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        if (narrow) AVD_CUDA(ctx, cudaFuncSetAttribute(k1_fused_kernel<128, K1_MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        else AVD_CUDA(ctx, cudaFuncSetAttribute(k1_fused_kernel<256, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         smem_set[narrow] = smem;
     }
     for (int f0 = 0; f0 < n; f0 += 65535) {                          // grid.y limit
@@ -485,8 +503,8 @@ int k1_fused(avd_ctx *ctx, const uint8_t *d_bgr, int n, int H, int W, size_t pit
         K1Params Q = P;
         Q.bgr = d_bgr + (size_t)f0 * fstride; Q.rec = d_rec + f0;
         Q.thumbs = d_thumbs + (size_t)f0 * AVD_T * AVD_T; Q.area32 = d_area32 + (size_t)f0 * 1024;
-        if (narrow) AVD_LAUNCH(ctx, "k1_fused", st, (k1_fused_kernel<160, K1_MINB><<<dim3(AVD_D, nb), threads, smem, st>>>(Q)));
-        else AVD_LAUNCH(ctx, "k1_fused", st, (k1_fused_kernel<288, 2><<<dim3(AVD_D, nb), threads, smem, st>>>(Q)));
+        if (narrow) AVD_LAUNCH(ctx, "k1_fused", st, (k1_fused_kernel<128, K1_MINB><<<dim3(AVD_D, nb), threads, smem, st>>>(Q)));
+        else AVD_LAUNCH(ctx, "k1_fused", st, (k1_fused_kernel<256, 2><<<dim3(AVD_D, nb), threads, smem, st>>>(Q)));
     }
     return AVD_OK;
 }
