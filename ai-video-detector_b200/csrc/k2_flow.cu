@@ -246,102 +246,103 @@ __global__ void __launch_bounds__(256) update_matrices_kernel(const float *__res
 }
 
 // ---- 15x15 box sums (float64) + 2x2 solve -------------------------------------------------------------
-constexpr int BS_TW = 32, BS_TH = 32, BS_M = 7, BS_CW = BS_TW + 2 * BS_M;   // 46 columns incl. halo
-constexpr int BS_PITCH = BS_CW + 1;
+// Warp-autonomous marching kernel: no shared memory, no block barriers.
+// A warp owns a strip of 128 columns (4 per lane; lanes 2..29 produce the 112 output columns, lanes 0,1,30,31
+// are the 8-column halo >= 7) and a segment of BX_SEG rows.  It marches down the segment keeping, per lane,
+// the vertical 15-row running sums of its 4 columns x 5 channels in float64 registers (run += new row - old
+// row: 2 adds per pixel-channel instead of 15).  The horizontal 15-column window is assembled from warp
+// shuffles of per-lane partial sums: window(j) = [T(t-1)+T(t)+T(t+1)] + suffix_{t-2}(j+1) + prefix_{t+2}(j).
+// float64 sums of <=225 float32 values are exact to ~1e-16, so any summation order agrees with the library's.
+// STATS: the last iteration of the finest level also emits per-task sums of |flow| and |flow|^2.
+constexpr int BX_SEG = 32, BX_COLS = 112, BX_WARPS = 4, BS_M = 7;
+__host__ __device__ constexpr int bx_strips(int s) { return (s + BX_COLS - 1) / BX_COLS; }
+__host__ __device__ constexpr int bx_segs(int s) { return (s + BX_SEG - 1) / BX_SEG; }
 
-// Tile 32x32 outputs.  (0) the M tile with its 7-pixel replicated halo goes to shared memory with fully
-// parallel coalesced loads; (1) vertical 15-row sliding sums, one thread per (channel, column), float64;
-// (2) horizontal 15-column sliding sums in place, one thread per (channel, row); (3) the 2x2 solve.
-// Sliding windows cost 2 adds per (pixel, channel, axis) instead of 15; float64 sums of <=225 float32
-// values are exact to ~1e-16, so the order of summation does not matter (the library uses running sums too).
-// STATS: the last iteration of the finest level also emits per-tile sums of |flow| and |flow|^2.
-constexpr int BS_TILE_F = 5 * BS_CW * BS_PITCH;            // floats of the staged M tile
-constexpr int BS_TILE_D = 5 * BS_TH * BS_PITCH;            // doubles of the sliding sums
+__device__ __forceinline__ float4 ld_row4(const float *__restrict__ rowp, int xa, int xb, int s)
+{
+    // 4 consecutive columns starting at xb (a multiple of 4); columns outside [0,s) replicate the edge column
+    float4 q = *(const float4 *)(rowp + xa);            // xa = clamp(xb, 0, s-4): always in range and 16-byte aligned
+    if (xb < 0) q = make_float4(q.x, q.x, q.x, q.x);
+    else if (xb >= s) q = make_float4(q.w, q.w, q.w, q.w);
+    return q;
+}
 
 template <bool STATS>
-__global__ void __launch_bounds__(256) blur_solve_kernel(const float *__restrict__ Mall, float *__restrict__ flow, int k,
-                                                         double *__restrict__ tile_stats)
+__global__ void __launch_bounds__(32 * BX_WARPS) box_solve_kernel(const float *__restrict__ Mall, float *__restrict__ flow, int k,
+                                                                 int n_pairs, double *__restrict__ task_stats)
 {
     const int s = lvl_size(k);
-    extern __shared__ double vs[];                         // [5][BS_TH][BS_PITCH] doubles, then the float tile
-    float *mt = (float *)(vs + BS_TILE_D);                 // [5][BS_CW rows][BS_PITCH]
-    const int x0 = blockIdx.x * BS_TW, y0 = blockIdx.y * BS_TH, p = blockIdx.z;
+    const int lane = threadIdx.x & 31;
+    const int tasks_per_pair = bx_strips(s) * bx_segs(s);
+    const int task = blockIdx.x * BX_WARPS + (threadIdx.x >> 5);
+    if (task >= tasks_per_pair * n_pairs) return;
+    const int p = task / tasks_per_pair, tp = task - p * tasks_per_pair;
+    const int strip = tp % bx_strips(s), seg = tp / bx_strips(s);
+    const int xb = strip * BX_COLS - 8 + 4 * lane, xa = clampi(xb, 0, s - 4);
+    const int y0 = seg * BX_SEG, y1 = min(y0 + BX_SEG, s);
     const size_t plane = (size_t)s * s;
     const float *M = Mall + (size_t)p * 5 * T * T;
-    const int tid = threadIdx.y * 32 + threadIdx.x;
-    {   // stage the tile: warp w takes rows w, w+8, ...; lanes take columns lane and lane+32 (no divisions)
-        const int lane = threadIdx.x, w = threadIdx.y;
-        const int gxa = clampi(x0 + lane - BS_M, 0, s - 1), gxb = clampi(x0 + lane + 32 - BS_M, 0, s - 1);
-        const bool hasb = lane + 32 < BS_CW;
-#pragma unroll 2
-        for (int row = w; row < BS_CW; row += 8) {
-            const float *src = M + (size_t)clampi(y0 + row - BS_M, 0, s - 1) * s;
-            float *dst = mt + row * BS_PITCH + lane;
+    const bool out_lane = lane >= 2 && lane < 30 && xb >= 0 && xb < s;
+
+    double run[5][4];
 #pragma unroll
-            for (int c = 0; c < 5; c++) {
-                dst[c * BS_CW * BS_PITCH] = src[c * plane + gxa];
-                if (hasb) dst[c * BS_CW * BS_PITCH + 32] = src[c * plane + gxb];
-            }
+    for (int c = 0; c < 5; c++) { run[c][0] = run[c][1] = run[c][2] = run[c][3] = 0.0; }
+    for (int j = -BS_M; j <= BS_M; j++) {
+        const float *rowp = M + (size_t)clampi(y0 + j, 0, s - 1) * s;
+#pragma unroll
+        for (int c = 0; c < 5; c++) {
+            float4 q = ld_row4(rowp + c * plane, xa, xb, s);
+            run[c][0] += (double)q.x; run[c][1] += (double)q.y; run[c][2] += (double)q.z; run[c][3] += (double)q.w;
         }
     }
-    __syncthreads();
-    if (tid < 5 * BS_CW) {
-        const int c = tid / BS_CW, col = tid - c * BS_CW;
-        const float *m = mt + c * BS_CW * BS_PITCH + col;
-        double run = 0;
-#pragma unroll
-        for (int j = 0; j < 15; j++) run += (double)m[j * BS_PITCH];
-#pragma unroll 4
-        for (int r = 0; r < BS_TH; r++) {
-            vs[(c * BS_TH + r) * BS_PITCH + col] = run;
-            if (r + 15 < BS_CW) run += (double)m[(r + 15) * BS_PITCH] - (double)m[r * BS_PITCH];
-        }
-    }
-    __syncthreads();
-    if (tid < 5 * BS_TH) {
-        double *v = vs + tid * BS_PITCH;                   // tid = c*BS_TH + row
-        double run = 0;
-#pragma unroll
-        for (int j = 0; j < 15; j++) run += v[j];
-#pragma unroll 4
-        for (int x = 0; x < BS_TW; x++) {
-            double old = v[x], nxt = x + 15 < BS_CW ? v[x + 15] : 0.0;
-            v[x] = run;
-            run += nxt - old;
-        }
-    }
-    __syncthreads();
-    const int x = x0 + threadIdx.x;
     const double scale = 1.0 / 225.0;
     double sm = 0, sq = 0;
-    for (int ry = threadIdx.y; ry < BS_TH; ry += 8) {
-        const int y = y0 + ry;
-        if (x >= s || y >= s) continue;
-        double a[5];
+    for (int y = y0; y < y1; y++) {
+        double a[5][4];
 #pragma unroll
-        for (int c = 0; c < 5; c++) a[c] = vs[(c * BS_TH + ry) * BS_PITCH + threadIdx.x] * scale;
-        double idet = 1.0 / (a[0] * a[2] - a[1] * a[1] + 1e-3);
-        size_t o = (size_t)y * s + x;
-        float fx = (float)((a[0] * a[4] - a[1] * a[3]) * idet), fy = (float)((a[2] * a[3] - a[1] * a[4]) * idet);
-        flow[(size_t)p * 2 * plane + o] = fx;
-        flow[(size_t)p * 2 * plane + plane + o] = fy;
-        if (STATS) {
-            double mag = (double)sqrtf(fx * fx + fy * fy);  // float32 magnitude like np.sqrt(fx**2+fy**2)
-            sm += mag; sq += mag * mag;
+        for (int c = 0; c < 5; c++) {
+            const double v0 = run[c][0], v1 = run[c][1], v2 = run[c][2], v3 = run[c][3];
+            const double tot = (v0 + v1) + (v2 + v3);
+            const double mid = __shfl_up_sync(0xffffffffu, tot, 1) + tot + __shfl_down_sync(0xffffffffu, tot, 1);
+            const double l1 = __shfl_up_sync(0xffffffffu, v1, 2), l2 = __shfl_up_sync(0xffffffffu, v2, 2), l3 = __shfl_up_sync(0xffffffffu, v3, 2);
+            const double r0 = __shfl_down_sync(0xffffffffu, v0, 2), r1 = __shfl_down_sync(0xffffffffu, v1, 2), r2 = __shfl_down_sync(0xffffffffu, v2, 2);
+            const double s3 = l3, s2 = l2 + l3, s1 = l1 + s2;       // suffix sums of lane t-2 from local index 3,2,1
+            const double p1 = r0, p2 = r0 + r1, p3 = p2 + r2;       // prefix sums of lane t+2 of 1,2,3 columns
+            a[c][0] = (mid + s1) * scale;
+            a[c][1] = (mid + s2 + p1) * scale;
+            a[c][2] = (mid + s3 + p2) * scale;
+            a[c][3] = (mid + p3) * scale;
+        }
+        if (out_lane) {
+            float fx[4], fy[4];
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const double g11 = a[0][j], g12 = a[1][j], g22 = a[2][j], h1 = a[3][j], h2 = a[4][j];
+                const double idet = 1.0 / (g11 * g22 - g12 * g12 + 1e-3);
+                fx[j] = (float)((g11 * h2 - g12 * h1) * idet);
+                fy[j] = (float)((g22 * h1 - g12 * h2) * idet);
+                if (STATS) {
+                    const double mag = (double)sqrtf(fx[j] * fx[j] + fy[j] * fy[j]);   // float32 magnitude like np.sqrt(fx**2+fy**2)
+                    sm += mag; sq += mag * mag;
+                }
+            }
+            float *fo = flow + (size_t)p * 2 * plane + (size_t)y * s + xb;
+            *(float4 *)fo = make_float4(fx[0], fx[1], fx[2], fx[3]);
+            *(float4 *)(fo + plane) = make_float4(fy[0], fy[1], fy[2], fy[3]);
+        }
+        // slide the vertical window: + row y+8, - row y-7 (replicated borders)
+        const float *rn = M + (size_t)min(y + BS_M + 1, s - 1) * s, *ro = M + (size_t)max(y - BS_M, 0) * s;
+#pragma unroll
+        for (int c = 0; c < 5; c++) {
+            const float4 qn = ld_row4(rn + c * plane, xa, xb, s), qo = ld_row4(ro + c * plane, xa, xb, s);
+            run[c][0] += (double)qn.x - (double)qo.x; run[c][1] += (double)qn.y - (double)qo.y;
+            run[c][2] += (double)qn.z - (double)qo.z; run[c][3] += (double)qn.w - (double)qo.w;
         }
     }
     if (STATS) {
-        // deterministic: fixed-order block reduction, one partial per tile, summed in tile order afterwards
+        // deterministic: fixed-order warp reduction, one partial per task, summed in task order afterwards
         for (int o = 16; o; o >>= 1) { sm += __shfl_down_sync(0xffffffffu, sm, o); sq += __shfl_down_sync(0xffffffffu, sq, o); }
-        __syncthreads();
-        if (threadIdx.x == 0) { vs[threadIdx.y] = sm; vs[8 + threadIdx.y] = sq; }
-        __syncthreads();
-        if (tid == 0) {
-            double a = 0, b = 0;
-            for (int w = 0; w < 8; w++) { a += vs[w]; b += vs[8 + w]; }
-            size_t t = ((size_t)p * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
-            tile_stats[2 * t] = a; tile_stats[2 * t + 1] = b;
-        }
+        if (lane == 0) { task_stats[2 * (size_t)task] = sm; task_stats[2 * (size_t)task + 1] = sq; }
     }
 }
 
@@ -439,7 +440,7 @@ FlowConst make_consts()
 
 // Workspace per batch of NI images / NP pairs (floats):
 //   pyr  NI*136000 | R  NI*136000*5 | M  NP*5*320*320 | flowA, flowB  NP*2*320*320 each | tile stats NP*100*2 doubles
-constexpr int STAT_TILES = (T / BS_TW) * (T / BS_TH);
+constexpr int STAT_TILES = bx_strips(T) * bx_segs(T);    // tasks per pair at the finest level
 static size_t k2_ws_bytes(int ni, int np)
 {
     return sizeof(float) * ((size_t)ni * PYR_PX * 6 + (size_t)np * T * T * 9) + sizeof(double) * 2 * STAT_TILES * (size_t)np;
@@ -461,13 +462,6 @@ int k2_flow(avd_ctx *ctx, const uint8_t *d_prev, const uint8_t *d_next, size_t p
     int rc;
     int cap_np = n_pairs < MAXP ? n_pairs : MAXP, cap_ni = shared_chain ? cap_np + 1 : 2 * cap_np;
     if ((rc = avd_ensure(ctx, &ctx->k2_ws, &ctx->k2_ws_cap, k2_ws_bytes(cap_ni, cap_np)))) return rc;
-    static bool attr_done = false;
-    size_t bs_smem = sizeof(double) * BS_TILE_D + sizeof(float) * BS_TILE_F;
-    if (!attr_done) {
-        AVD_CUDA(ctx, cudaFuncSetAttribute(blur_solve_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bs_smem));
-        AVD_CUDA(ctx, cudaFuncSetAttribute(blur_solve_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bs_smem));
-        attr_done = true;
-    }
     for (int p0 = 0; p0 < n_pairs; p0 += MAXP) {
         int np = n_pairs - p0 < MAXP ? n_pairs - p0 : MAXP;
         int ni = shared_chain ? np + 1 : 2 * np;
@@ -497,7 +491,7 @@ int k2_flow(avd_ctx *ctx, const uint8_t *d_prev, const uint8_t *d_next, size_t p
         for (int k = 3; k >= 0; k--) {
             int s = lvl_size(k);
             dim3 gu((s + 31) / 32, (s + 7) / 8, np), bu(32, 8);
-            dim3 gb((s + BS_TW - 1) / BS_TW, (s + BS_TH - 1) / BS_TH, np);
+            const int bx_blocks = (bx_strips(s) * bx_segs(s) * np + BX_WARPS - 1) / BX_WARPS;
             if (k == 3) {
                 AVD_LAUNCH(ctx, "update_matrices", st, update_matrices_kernel<0><<<gu, bu, 0, st>>>(R, nullptr, nullptr, M, nullptr, k, mode));
             } else {
@@ -505,9 +499,9 @@ int k2_flow(avd_ctx *ctx, const uint8_t *d_prev, const uint8_t *d_next, size_t p
             }
             for (int it = 0; it < 3; it++) {
                 if (k == 0 && it == 2 && d_rec_first) {
-                    AVD_LAUNCH(ctx, "blur_solve", st, blur_solve_kernel<true><<<gb, bu, bs_smem, st>>>(M, cur, k, tile_stats));
+                    AVD_LAUNCH(ctx, "box_solve", st, box_solve_kernel<true><<<bx_blocks, 32 * BX_WARPS, 0, st>>>(M, cur, k, np, tile_stats));
                 } else {
-                    AVD_LAUNCH(ctx, "blur_solve", st, blur_solve_kernel<false><<<gb, bu, bs_smem, st>>>(M, cur, k, nullptr));
+                    AVD_LAUNCH(ctx, "box_solve", st, box_solve_kernel<false><<<bx_blocks, 32 * BX_WARPS, 0, st>>>(M, cur, k, np, nullptr));
                 }
                 if (it < 2) {
                     AVD_LAUNCH(ctx, "update_matrices", st, update_matrices_kernel<1><<<gu, bu, 0, st>>>(R, cur, nullptr, M, nullptr, k, mode));
