@@ -138,3 +138,32 @@ def analyze(path: str, meta: dict, engine=None) -> dict:
     recs = np.concatenate(runs) if runs else np.zeros(0, REC_DTYPE)
     H, W = (shape[0], shape[1]) if shape else (int(h), int(w))
     return result_from_records(recs, H, W, fps, duration, w=w, h=h)
+
+
+def analyze_frames_batch(clips, metas, engine=None):
+    """A batch of independent clips (BASELINE configs[3]): ``clips[i]`` are the sampled frames of clip i (all
+    clips one frame size), ``metas[i]`` its meta dict.  All frames go through the device in ONE run; the
+    records at clip boundaries are then detached from their (foreign) predecessor, which is exactly the state
+    video.py starts every clip with (prev_hash = None, prev_frame_small = None; video.py:20,26).
+    Returns one result dict per clip."""
+    eng = engine or default_engine()
+    frames, starts = [], []
+    for c in clips:
+        starts.append(len(frames))
+        frames.extend(c[i] for i in range(len(c)))
+    recs = eng.analyze_host(frames) if frames else np.zeros(0, REC_DTYPE)
+    out = []
+    for ci, c in enumerate(clips):
+        n = len(c)
+        r = recs[starts[ci]:starts[ci] + n].copy()
+        if n:
+            r["ham_prev"][0] = -1
+            r["flags"][0] = 0
+            r["flow_mean"][0] = 0.0
+            r["flow_var"][0] = 0.0
+        meta = metas[ci]
+        fps = meta.get("fps") or 0.0
+        H, W = (int(c[0].shape[0]), int(c[0].shape[1])) if n else (0, 0)
+        duration = meta.get("duration") or (n * sample_step(fps) / fps if fps > 0 else 0.0)
+        out.append(result_from_records(r, H, W, fps, duration, w=meta.get("width") or W, h=meta.get("height") or H))
+    return out
