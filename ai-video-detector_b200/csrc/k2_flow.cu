@@ -11,6 +11,7 @@
 // Compiled with -fmad=false: the float sequences round exactly like the scalar library code.
 #include "avd_internal.h"
 #include <math.h>
+#include <stdlib.h>
 
 namespace {
 
@@ -193,10 +194,10 @@ __device__ __forceinline__ float up2_sample(const float *__restrict__ c, int cs,
 template <int FLOWSRC>
 __global__ void __launch_bounds__(256) update_matrices_kernel(const float *__restrict__ Rall, const float *__restrict__ flow,
                                                               const float *__restrict__ coarse, float *__restrict__ Mall,
-                                                              float *__restrict__ flow_store, int k, int pair_img_mode)
+                                                              float *__restrict__ flow_store, int k, int pair_img_mode, int p_base)
 {
     const int s = lvl_size(k);
-    int x = blockIdx.x * 32 + threadIdx.x, y = blockIdx.y * 8 + threadIdx.y, p = blockIdx.z;
+    int x = blockIdx.x * 32 + threadIdx.x, y = blockIdx.y * 8 + threadIdx.y, p = blockIdx.z + p_base;
     if (x >= s || y >= s) return;
     int ia = pair_img_mode == 2 ? 2 * p : p, ib = ia + 1;
     size_t plane = (size_t)s * s, o = (size_t)y * s + x;
@@ -261,7 +262,8 @@ __host__ __device__ constexpr int bx_segs(int s) { return (s + BX_SEG - 1) / BX_
 __device__ __forceinline__ float4 ld_row4(const float *__restrict__ rowp, int xa, int xb, int s)
 {
     // 4 consecutive columns starting at xb (a multiple of 4); columns outside [0,s) replicate the edge column
-    float4 q = *(const float4 *)(rowp + xa);            // xa = clamp(xb, 0, s-4): always in range and 16-byte aligned
+    float4 q;                                           // xa = clamp(xb, 0, s-4): always in range and 16-byte aligned
+    asm("ld.global.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(q.x), "=f"(q.y), "=f"(q.z), "=f"(q.w) : "l"(rowp + xa));
     if (xb < 0) q = make_float4(q.x, q.x, q.x, q.x);
     else if (xb >= s) q = make_float4(q.w, q.w, q.w, q.w);
     return q;
@@ -269,14 +271,14 @@ __device__ __forceinline__ float4 ld_row4(const float *__restrict__ rowp, int xa
 
 template <bool STATS>
 __global__ void __launch_bounds__(32 * BX_WARPS) box_solve_kernel(const float *__restrict__ Mall, float *__restrict__ flow, int k,
-                                                                 int n_pairs, double *__restrict__ task_stats)
+                                                                 int n_pairs, double *__restrict__ task_stats, int p_base)
 {
     const int s = lvl_size(k);
     const int lane = threadIdx.x & 31;
     const int tasks_per_pair = bx_strips(s) * bx_segs(s);
     const int task = blockIdx.x * BX_WARPS + (threadIdx.x >> 5);
     if (task >= tasks_per_pair * n_pairs) return;
-    const int p = task / tasks_per_pair, tp = task - p * tasks_per_pair;
+    const int pl = task / tasks_per_pair, tp = task - pl * tasks_per_pair, p = pl + p_base;
     const int strip = tp % bx_strips(s), seg = tp / bx_strips(s);
     const int xb = strip * BX_COLS - 8 + 4 * lane, xa = clampi(xb, 0, s - 4);
     const int y0 = seg * BX_SEG, y1 = min(y0 + BX_SEG, s);
@@ -342,7 +344,7 @@ __global__ void __launch_bounds__(32 * BX_WARPS) box_solve_kernel(const float *_
     if (STATS) {
         // deterministic: fixed-order warp reduction, one partial per task, summed in task order afterwards
         for (int o = 16; o; o >>= 1) { sm += __shfl_down_sync(0xffffffffu, sm, o); sq += __shfl_down_sync(0xffffffffu, sq, o); }
-        if (lane == 0) { task_stats[2 * (size_t)task] = sm; task_stats[2 * (size_t)task + 1] = sq; }
+        if (lane == 0) { size_t t = (size_t)p * tasks_per_pair + tp; task_stats[2 * t] = sm; task_stats[2 * t + 1] = sq; }
     }
 }
 
@@ -488,23 +490,31 @@ int k2_flow(avd_ctx *ctx, const uint8_t *d_prev, const uint8_t *d_next, size_t p
             AVD_LAUNCH(ctx, "polyexp", st, polyexp_kernel<<<dim3((s + PE_TW - 1) / PE_TW, (s + PE_TH - 1) / PE_TH, ni), dim3(PE_TW, PE_TH), 0, st>>>(pyr, R, k));
         }
         float *cur = flowA, *prev = flowB;
+        // Levels 0 and 1 run in sub-batches of pairs sized so that R (both images), M and the flow of a sub-batch
+        // stay L2-resident across the 6 kernels of a level (update/solve x3) instead of streaming 119 pairs
+        // through HBM six times.  AVD_K2_SB0 / AVD_K2_SB1 override the sub-batch sizes (tuning).
+        static int sb0 = getenv("AVD_K2_SB0") ? atoi(getenv("AVD_K2_SB0")) : 12, sb1 = getenv("AVD_K2_SB1") ? atoi(getenv("AVD_K2_SB1")) : 48;
         for (int k = 3; k >= 0; k--) {
-            int s = lvl_size(k);
-            dim3 gu((s + 31) / 32, (s + 7) / 8, np), bu(32, 8);
-            const int bx_blocks = (bx_strips(s) * bx_segs(s) * np + BX_WARPS - 1) / BX_WARPS;
-            if (k == 3) {
-                AVD_LAUNCH(ctx, "update_matrices", st, update_matrices_kernel<0><<<gu, bu, 0, st>>>(R, nullptr, nullptr, M, nullptr, k, mode));
-            } else {
-                AVD_LAUNCH(ctx, "update_matrices", st, update_matrices_kernel<2><<<gu, bu, 0, st>>>(R, nullptr, prev, M, nullptr, k, mode));
-            }
-            for (int it = 0; it < 3; it++) {
-                if (k == 0 && it == 2 && d_rec_first) {
-                    AVD_LAUNCH(ctx, "box_solve", st, box_solve_kernel<true><<<bx_blocks, 32 * BX_WARPS, 0, st>>>(M, cur, k, np, tile_stats));
+            const int s = lvl_size(k);
+            const int SB = k == 0 ? (sb0 > 0 ? sb0 : np) : k == 1 ? (sb1 > 0 ? sb1 : np) : np;
+            for (int q0 = 0; q0 < np; q0 += SB) {
+                const int nq = np - q0 < SB ? np - q0 : SB;
+                dim3 gu((s + 31) / 32, (s + 7) / 8, nq), bu(32, 8);
+                const int bx_blocks = (bx_strips(s) * bx_segs(s) * nq + BX_WARPS - 1) / BX_WARPS;
+                if (k == 3) {
+                    AVD_LAUNCH(ctx, "update_matrices", st, update_matrices_kernel<0><<<gu, bu, 0, st>>>(R, nullptr, nullptr, M, nullptr, k, mode, q0));
                 } else {
-                    AVD_LAUNCH(ctx, "box_solve", st, box_solve_kernel<false><<<bx_blocks, 32 * BX_WARPS, 0, st>>>(M, cur, k, np, nullptr));
+                    AVD_LAUNCH(ctx, "update_matrices", st, update_matrices_kernel<2><<<gu, bu, 0, st>>>(R, nullptr, prev, M, nullptr, k, mode, q0));
                 }
-                if (it < 2) {
-                    AVD_LAUNCH(ctx, "update_matrices", st, update_matrices_kernel<1><<<gu, bu, 0, st>>>(R, cur, nullptr, M, nullptr, k, mode));
+                for (int it = 0; it < 3; it++) {
+                    if (k == 0 && it == 2 && d_rec_first) {
+                        AVD_LAUNCH(ctx, "box_solve", st, box_solve_kernel<true><<<bx_blocks, 32 * BX_WARPS, 0, st>>>(M, cur, k, nq, tile_stats, q0));
+                    } else {
+                        AVD_LAUNCH(ctx, "box_solve", st, box_solve_kernel<false><<<bx_blocks, 32 * BX_WARPS, 0, st>>>(M, cur, k, nq, nullptr, q0));
+                    }
+                    if (it < 2) {
+                        AVD_LAUNCH(ctx, "update_matrices", st, update_matrices_kernel<1><<<gu, bu, 0, st>>>(R, cur, nullptr, M, nullptr, k, mode, q0));
+                    }
                 }
             }
             float *t = cur; cur = prev; prev = t;   // prev now holds this level's flow
