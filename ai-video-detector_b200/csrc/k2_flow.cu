@@ -263,7 +263,14 @@ __device__ __forceinline__ float4 ld_row4(const float *__restrict__ rowp, int xa
 {
     // 4 consecutive columns starting at xb (a multiple of 4); columns outside [0,s) replicate the edge column
     float4 q;                                           // xa = clamp(xb, 0, s-4): always in range and 16-byte aligned
+#ifndef K2_VEC_ASM
+#define K2_VEC_ASM 1
+#endif
+#if K2_VEC_ASM
     asm("ld.global.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(q.x), "=f"(q.y), "=f"(q.z), "=f"(q.w) : "l"(rowp + xa));
+#else
+    q = *(const float4 *)(rowp + xa);
+#endif
     if (xb < 0) q = make_float4(q.x, q.x, q.x, q.x);
     else if (xb >= s) q = make_float4(q.w, q.w, q.w, q.w);
     return q;
