@@ -264,7 +264,7 @@ __device__ __forceinline__ float4 ld_row4(const float *__restrict__ rowp, int xa
     // 4 consecutive columns starting at xb (a multiple of 4); columns outside [0,s) replicate the edge column
     float4 q;                                           // xa = clamp(xb, 0, s-4): always in range and 16-byte aligned
 #ifndef K2_VEC_ASM
-#define K2_VEC_ASM 1
+#define K2_VEC_ASM 0   /* measured: hand-placed ld.global.v4 doubles box_solve time (the compiler's own loads are software-pipelined) */
 #endif
 #if K2_VEC_ASM
     asm("ld.global.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(q.x), "=f"(q.y), "=f"(q.z), "=f"(q.w) : "l"(rowp + xa));
@@ -497,10 +497,10 @@ int k2_flow(avd_ctx *ctx, const uint8_t *d_prev, const uint8_t *d_next, size_t p
             AVD_LAUNCH(ctx, "polyexp", st, polyexp_kernel<<<dim3((s + PE_TW - 1) / PE_TW, (s + PE_TH - 1) / PE_TH, ni), dim3(PE_TW, PE_TH), 0, st>>>(pyr, R, k));
         }
         float *cur = flowA, *prev = flowB;
-        // Levels 0 and 1 run in sub-batches of pairs sized so that R (both images), M and the flow of a sub-batch
-        // stay L2-resident across the 6 kernels of a level (update/solve x3) instead of streaming 119 pairs
-        // through HBM six times.  AVD_K2_SB0 / AVD_K2_SB1 override the sub-batch sizes (tuning).
-        static int sb0 = getenv("AVD_K2_SB0") ? atoi(getenv("AVD_K2_SB0")) : 12, sb1 = getenv("AVD_K2_SB1") ? atoi(getenv("AVD_K2_SB1")) : 48;
+        // Optional L2-resident sub-batching of levels 0/1 (AVD_K2_SB0 / AVD_K2_SB1 = pairs per sub-batch, 0 = off).
+        // Measured on B200 (profiles/r01_k2_notes.md): OFF is faster -- box_solve has only 30 warps of work per pair,
+        // so a 16-pair sub-batch leaves most SMs idle (box_solve 1.06 -> 4.1 ms, update_matrices 0.69 -> 0.84 ms).
+        static int sb0 = getenv("AVD_K2_SB0") ? atoi(getenv("AVD_K2_SB0")) : 0, sb1 = getenv("AVD_K2_SB1") ? atoi(getenv("AVD_K2_SB1")) : 0;
         for (int k = 3; k >= 0; k--) {
             const int s = lvl_size(k);
             const int SB = k == 0 ? (sb0 > 0 ? sb0 : np) : k == 1 ? (sb1 > 0 ? sb1 : np) : np;
