@@ -240,7 +240,7 @@ int avd_profile_read(avd_ctx *ctx, char *buf, size_t cap)
 
 int avd_set_k1_mode(avd_ctx *ctx, int mode)
 {
-    if (!ctx || mode < 0 || mode > 1) return AVD_ERR_ARG;
+    if (!ctx || mode < 0 || mode > 2) return AVD_ERR_ARG;
     ctx->k1_mode = mode;
     return AVD_OK;
 }
@@ -272,8 +272,10 @@ int avd_frames_features(avd_ctx *ctx, const uint8_t *d_bgr, int n, int H, int W,
         d_area32 = ctx->area32;
     }
     if ((rc = k1_rec_init(ctx, d_rec, n, st))) return rc;
-    if (ctx->k1_mode == 0 && k1_fused_supported(H, W, row_pitch, frame_stride, d_bgr))
+    if (ctx->k1_mode == 0 && k1_fused_supported(H, W, row_pitch, frame_stride, d_bgr, htab))
         rc = k1_fused(ctx, d_bgr, n, H, W, row_pitch, frame_stride, tab, htab, d_rec, d_thumbs, d_area32, st);
+    else if ((ctx->k1_mode == 0 || ctx->k1_mode == 2) && k1_banded_supported(H, W, row_pitch, frame_stride, d_bgr))
+        rc = k1_banded(ctx, d_bgr, n, H, W, row_pitch, frame_stride, tab, htab, d_rec, d_thumbs, d_area32, st);
     else
         rc = k1_generic(ctx, d_bgr, n, H, W, row_pitch, frame_stride, tab, htab, d_rec, d_thumbs, d_area32, st);
     if (rc) return rc;

@@ -108,8 +108,12 @@ int k1_generic(avd_ctx *ctx, const uint8_t *d_bgr, int n, int H, int W, size_t p
 int k1_gray_only(avd_ctx *ctx, const uint8_t *d_bgr, int H, int W, size_t pitch, uint8_t *d_gray, cudaStream_t st);
 int k1_hash_finalize(avd_ctx *ctx, const uint8_t *d_area32, int n, const uint32_t *d_prev_hash,
                      avd_sample_rec *d_rec, cudaStream_t st);
-// k1_fused.cu
-bool k1_fused_supported(int H, int W, size_t pitch, size_t fstride, const void *base);
+// k1_fused.cu (streaming kernel: W % 64 == 0, 640 <= W <= 4096, 640 <= H <= 4096) and k1_banded.cu (W % 16 == 0)
+bool k1_fused_supported(int H, int W, size_t pitch, size_t fstride, const void *base, const ShapeTables *htab);
+bool k1_banded_supported(int H, int W, size_t pitch, size_t fstride, const void *base);
+int k1_banded(avd_ctx *ctx, const uint8_t *d_bgr, int n, int H, int W, size_t pitch, size_t fstride,
+              const ShapeTables *tab, const ShapeTables *htab, avd_sample_rec *d_rec, uint8_t *d_thumbs,
+              uint8_t *d_area32, cudaStream_t st);
 int k1_fused(avd_ctx *ctx, const uint8_t *d_bgr, int n, int H, int W, size_t pitch, size_t fstride,
              const ShapeTables *tab, const ShapeTables *htab, avd_sample_rec *d_rec, uint8_t *d_thumbs,
              uint8_t *d_area32, cudaStream_t st);

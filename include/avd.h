@@ -119,8 +119,9 @@ uint64_t avd_launch_count(const avd_ctx *ctx);
 int avd_profile_enable(avd_ctx *ctx, int on);
 int avd_profile_read(avd_ctx *ctx, char *buf, size_t cap);
 
-/* Select the per-frame kernel: 0 = auto (fused TMA path when W % 16 == 0 and buffers are 16-byte
- * aligned, generic otherwise), 1 = force generic multi-kernel path.  For tests. */
+/* Select the per-frame kernel: 0 = auto (streaming fused kernel when W % 64 == 0, 640 <= W,H <= 4096 and buffers
+ * are 16-byte aligned; banded fused kernel when W % 16 == 0; generic otherwise), 1 = force the generic
+ * multi-kernel path, 2 = skip the streaming kernel (banded or generic).  For tests. */
 int avd_set_k1_mode(avd_ctx *ctx, int mode);
 
 #ifdef __cplusplus

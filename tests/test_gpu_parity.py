@@ -52,11 +52,12 @@ def test_extension_is_loaded_and_native(eng):
     assert eng.launches == 0
 
 
-@pytest.mark.parametrize("mode", [0, 1])
+@pytest.mark.parametrize("mode", [0, 1, 2])
 @pytest.mark.parametrize("idx", range(13))
 def test_frame_features_vs_reference_golden(golden, golden_arrays, synth, torch, eng, idx, mode):
     """Every library code path (general / integer INTER_AREA, 2x2 INTER_LINEAR shortcut, upsampling, odd
-    widths, 32x32 minimum, 4K) against what cv2 produced for the reference; both K1 implementations."""
+    widths, 32x32 minimum, 4K) against what cv2 produced for the reference; all three K1 implementations
+    (0 = streaming fused kernel where the shape allows, 1 = generic, 2 = banded fused kernel)."""
     c = golden["frames"][idx]
     f = _frame(synth, c)
     eng.set_k1_mode(mode)
@@ -75,17 +76,44 @@ def test_frame_features_vs_reference_golden(golden, golden_arrays, synth, torch,
 
 
 def test_fused_equals_generic_on_batches(synth, torch, eng):
-    """The two K1 implementations must agree byte for byte on a batch (incl. Hamming chain)."""
-    for (H, W) in [(720, 1280), (1080, 1920), (96, 128), (270, 480), (360, 640)]:
+    """The three K1 implementations must agree byte for byte on a batch (incl. Hamming chain)."""
+    for (H, W) in [(720, 1280), (1080, 1920), (96, 128), (270, 480), (360, 640), (960, 1280), (1440, 2560), (2160, 3840),
+                   (648, 704), (1000, 4096)]:
         clip = synth.Clip(40, H, W, seed=5, events=True)
         fr = torch.from_numpy(np.stack([clip[i] for i in (0, 3, 12, 13, 20, 25, 31, 39)])).cuda()
         outs = []
-        for mode in (0, 1):
+        for mode in (0, 1, 2):
             eng.set_k1_mode(mode)
             rec, th, ar = eng.frames_features(fr, want_area32=True)
             outs.append((rec.cpu().numpy().tobytes(), th.cpu().numpy().tobytes(), ar.cpu().numpy().tobytes()))
         eng.set_k1_mode(0)
-        assert outs[0] == outs[1], (H, W)
+        assert outs[0] == outs[1], (H, W, "streaming vs generic")
+        assert outs[2] == outs[1], (H, W, "banded vs generic")
+
+
+def test_area_rounding_boundaries(torch, eng, oracle):
+    """INTER_AREA cells whose exact mean sits on or next to a rounding boundary (k + 0.5): the streaming kernel
+    must fall back to the library's float32 summation order for them and still be bit-exact with the oracle."""
+    rng = np.random.default_rng(11)
+    H, W = 1080, 1920
+    frames = []
+    g = np.full((H, W), 100, np.uint8); g[:, 1::2] = 101; frames.append(g)               # every cell mean = 100.5
+    g = np.full((H, W), 7, np.uint8); g[::2, :] = 8; frames.append(g)                     # row stripes, fractional rows
+    g = (100 + (rng.random((H, W)) < 0.5)).astype(np.uint8); frames.append(g)             # means scattered around 100.5
+    g = rng.integers(0, 256, (H, W), dtype=np.uint8); g[:540] = (g[:540] & 1) + 200; frames.append(g)
+    g = np.full((H, W), 255, np.uint8); g[:, ::2] = 254; frames.append(g)                 # 254.5: saturation side
+    bgr = np.stack([np.repeat(x[:, :, None], 3, axis=2) for x in frames])                 # B=G=R=v -> gray = v
+    d = torch.from_numpy(bgr).cuda()
+    outs = {}
+    for mode in (0, 1):
+        eng.set_k1_mode(mode)
+        rec, th, ar = eng.frames_features(d, want_area32=True)
+        outs[mode] = (rec.cpu().numpy().tobytes(), ar.cpu().numpy())
+    eng.set_k1_mode(0)
+    for i, x in enumerate(frames):
+        assert np.array_equal(eng.gray(d[i]).cpu().numpy(), x)
+        assert np.array_equal(outs[0][1][i], oracle.area32(x)), i
+    assert outs[0][0] == outs[1][0] and np.array_equal(outs[0][1], outs[1][1])
 
 
 def test_padded_pitch_and_unaligned_views(synth, torch, eng, oracle):
