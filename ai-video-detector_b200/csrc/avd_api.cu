@@ -82,6 +82,15 @@ int avd_get_tables(avd_ctx *ctx, int H, int W, const ShapeTables **dev, const Sh
             while (ty < AVD_T && (t.thumb_2x2 ? 2 * ty : t.ly[ty].i0) < t.row_owner_begin[b + 1]) ty++;
         }
         t.thumb_row_begin[AVD_D] = AVD_T;
+        // thumbnail columns per 16-pixel strip (streaming kernel)
+        t.strip_ntx_max = 0;
+        for (int s = 0, tx = 0; s < 256; s++) {
+            while (tx < AVD_T && t.lx[tx].i0 < 16 * s) tx++;
+            int cnt = 0;
+            while (tx + cnt < AVD_T && t.lx[tx + cnt].i0 < 16 * s + 16) cnt++;
+            t.strip_tx0[s] = (uint16_t)tx; t.strip_ntx[s] = (uint8_t)(cnt > 255 ? 255 : cnt);
+            if (16 * s < W && cnt > t.strip_ntx_max) t.strip_ntx_max = cnt;
+        }
         ShapeTables *d = nullptr;
         AVD_CUDA(ctx, cudaMalloc(&d, sizeof(ShapeTables)));
         AVD_CUDA(ctx, cudaMemcpy(d, &t, sizeof(ShapeTables), cudaMemcpyHostToDevice));

@@ -36,6 +36,10 @@ struct ShapeTables {
     int thumb_2x2;           // source is exactly 640x640 -> 2x2 mean
     int row_owner_begin[AVD_D + 1];  // first source row owned by band b (fused kernel); [32] = H
     int thumb_row_begin[AVD_D + 1];  // first thumbnail row whose top tap lies in band b; [32] = 320
+    // streaming kernel: thumbnail columns whose left tap lies in the 16-pixel strip s (first column, count)
+    uint16_t strip_tx0[256];
+    uint8_t strip_ntx[256];
+    int strip_ntx_max;
 };
 
 struct avd_ctx {

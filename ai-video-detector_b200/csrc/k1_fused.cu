@@ -18,8 +18,10 @@
 //                Laplacian   two pixels per register in 16-bit lanes, biased by +1020; sum of squares through
 //                            byte-split IDP.4A; the plain sum telescopes to strip/band borders
 //                INTER_AREA  exact integer cell sums (one IADD3 per 4 pixels) -- see "certificate" below
-//   thumb warp   one extra warp turns the tap rows of the thumbnail (written by the main warps into a small gray
-//                ring, handed over with mbarriers) into thumbnail rows, so the main warps never meet a block barrier
+//                thumbnail   the thread that owns a strip also owns the thumbnail columns whose left tap lies in
+//                            it: on tap rows it parks its 16 gray bytes (+ the right neighbour) in a private
+//                            48-byte shared-memory slot and reads the tap bytes back at its own dynamic offsets --
+//                            thread-private, so the warps never meet a block barrier inside the band
 //
 // INTER_AREA certificate.  The library accumulates float32 products sequentially; the result is
 // rounded to u8 and only that byte is observable.  The kernel computes the exact rational cell mean from integer
@@ -32,21 +34,20 @@
 namespace {
 
 #ifndef K1_NRS
-#define K1_NRS 3
+#define K1_NRS 6
 #endif
 #ifndef K1_MINB
 #define K1_MINB 4
 #endif
 constexpr int NRS = K1_NRS;           // single-row TMA stages per CTA (multiple of 3: stage index is static per unrolled step)
-static_assert(NRS == 3, "stage index is tied to the 3-way register rotation");
-constexpr int RP = 4;                 // tap-row pairs in the gray ring
-constexpr int MAXQ = 160;             // rows a band can load (H/32 + 3)
-constexpr int NTX = AVD_T / 32;       // thumbnail columns per lane of the thumb warp
+static_assert(NRS % 3 == 0 && NRS <= 6, "stages come in groups of 3: the position inside a group is tied to the 3-way register rotation");
+constexpr int NGRP = NRS / 3;
+constexpr int MAXQ = 132;             // rows a band can load (H/32 + 3, H <= 4096)
+constexpr int SLOT = 48;              // bytes of a thread's private gray slot (48: conflict-free 128-bit stores)
 
 // shared-memory header (bytes)
-constexpr int OFF_FULL = 0, OFF_RFULL = 64, OFF_REMPTY = 96, OFF_CNT = 128, OFF_MISC = 160, OFF_CELL = 256, OFF_RED = 384,
-              OFF_INFO = 576, HDR = 768;
-static_assert(OFF_INFO + MAXQ <= HDR, "header layout");
+constexpr int OFF_FULL = 0, OFF_CNT = 64, OFF_MISC = 192, OFF_CELL = 256, OFF_RED = 384, OFF_INFO = 512, HDR = 1040;
+static_assert(OFF_INFO + 4 * MAXQ <= HDR, "header layout");
 
 struct K1Params {
     const uint8_t *bgr;
@@ -77,13 +78,15 @@ __device__ __forceinline__ void tma_load_1d(uint32_t dst, const void *src, uint3
 }
 __device__ __noinline__ void mbar_wait_slow(uint32_t bar, uint32_t parity)
 {
-    const long long t0 = clock64();
-    while (true) {
+    // try_wait suspends the thread in hardware for up to the hinted time, so this loop turns over rarely;
+    // a lost refill must fail loudly instead of hanging the GPU
+    for (int it = 0; it < (1 << 22); it++) {
         uint32_t ok;
-        asm volatile("{\n.reg .pred P1;\nmbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\nselp.u32 %0, 1, 0, P1;\n}" : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+        asm volatile("{\n.reg .pred P1;\nmbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2, %3;\nselp.u32 %0, 1, 0, P1;\n}"
+                     : "=r"(ok) : "r"(bar), "r"(parity), "r"(20000u) : "memory");
         if (ok) return;
-        if (clock64() - t0 > 4000000000ll) __trap();     // ~2 s: a lost refill must fail loudly, not hang the GPU
     }
+    __trap();
 }
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
 {
@@ -92,14 +95,14 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
     if (!ok) mbar_wait_slow(bar, parity);
 }
 // lane 0 of a warp counts the warp off a stage; returns 1 in the lane that arrived last (pending count before its arrival)
-__device__ __forceinline__ uint32_t stage_arrive(uint32_t bar, uint32_t lane0)
+// `dep` is a value computed from the last bytes loaded from the stage: the arrival cannot be issued before they landed
+__device__ __forceinline__ uint32_t stage_arrive(uint32_t bar, uint32_t lane0, uint32_t dep)
 {
     uint32_t pend = 0;
     asm volatile("{\n.reg .pred p;\n.reg .b64 st;\nsetp.ne.u32 p, %2, 0;\n@p mbarrier.arrive.shared::cta.b64 st, [%1];\n@p mbarrier.pending_count.b64 %0, st;\n}"
-                 : "+r"(pend) : "r"(bar), "r"(lane0) : "memory");
+                 : "+r"(pend) : "r"(bar), "r"(lane0), "r"(dep) : "memory");
     return pend;
 }
-__device__ __forceinline__ void main_sync(int n) { asm volatile("bar.sync 1, %0;" ::"r"(n) : "memory"); }
 
 // 2*(3735,19235,9798): the doubled 15-bit weights; acc = 2*(...)+32768 so gray = acc >> 16 = byte 2
 constexpr uint32_t WB = 7470u, WG = 38470u, WR = 19596u;
@@ -155,7 +158,7 @@ __device__ __forceinline__ void lap_step(const RowSet &U, const RowSet &C, const
 struct Band {
     uint32_t sbase;                       // shared address of the header
     uint32_t stage;                       // shared address of stage 0
-    uint8_t *ring;                        // gray ring (generic pointer)
+    uint32_t slot;                        // shared address of this thread's private gray slot
     int row_bytes, W, H, own0, nseq, nw;
     const uint8_t *frame;
     size_t pitch;
@@ -167,18 +170,28 @@ __device__ __forceinline__ void issue_row(const Band &B, int q, int s)
 {
     int r = B.own0 - 1 + q;
     r = r < 0 ? 1 : (r >= B.H ? B.H - 2 : r);
-    const uint32_t bar = B.sbase + OFF_FULL + 8 * s;
+    const uint32_t bar = B.sbase + OFF_FULL + 8 * s;   // s = 3 * group + position
     mbar_expect_tx(bar, (uint32_t)B.row_bytes);
     // the two first and two last rows of a band are also read by the neighbouring bands: do not mark them evict-first
     const bool shared_row = q < 2 || q >= B.nseq - 2;
     tma_load_1d(B.stage + s * B.row_bytes, B.frame + (size_t)r * B.pitch, (uint32_t)B.row_bytes, bar, shared_row ? B.pol_keep : B.pol_stream);
 }
 
-// Stage s holds sequence row q: convert this thread's strip to gray (row set R); tap rows of the thumbnail also go
-// to the gray ring.  Returns the stage's arrival ticket of this warp (lane 0), to be passed to release_finish.
-template <int S>
-__device__ __forceinline__ uint32_t load_row(const Band &B, int q, uint32_t parity, int tid, bool active, bool first, bool last, RowSet &R)
+// thumbnail columns owned by this thread (left tap inside its strip): shared address of the left tap byte in the
+// thread's slot, the two horizontal weights, the vertically weighted first tap row carried to the second
+template <int JT> struct Thumb {
+    uint32_t addr[JT], a0[JT], a1[JT], u0[JT];
+    int ntx;
+    uint8_t *dst;                          // &thumbs[frame][0][first column of this thread]
+};
+
+// Stage s holds sequence row q: convert this thread's strip to gray (row set R); on tap rows of the thumbnail also
+// advance this thread's thumbnail columns.  Returns 1 in lane 0 of the warp that was last to leave the stage
+// (passed on to release_finish).
+template <int POS, int JT>
+__device__ __forceinline__ uint32_t load_row(const Band &B, int q, int grp, uint32_t parity, int tid, bool first, bool last, RowSet &R, Thumb<JT> &T)
 {
+    const int S = 3 * grp + POS;
     mbar_wait(B.sbase + OFF_FULL + 8 * S, parity);
     const uint32_t sp = B.stage + S * B.row_bytes + 48 * tid;
     uint4 q0, q1, q2;
@@ -188,9 +201,6 @@ __device__ __forceinline__ uint32_t load_row(const Band &B, int q, uint32_t pari
     asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4+32];" : "=r"(q2.x), "=r"(q2.y), "=r"(q2.z), "=r"(q2.w) : "r"(sp));
     asm volatile("ld.shared.u32 %0, [%1+-4];" : "=r"(wl) : "r"(sp));
     asm volatile("ld.shared.u32 %0, [%1+48];" : "=r"(wr) : "r"(sp));
-    // every lane of this warp has its bytes in registers: count the warp off the stage (result used much later)
-    __syncwarp();
-    const uint32_t ticket = stage_arrive(B.sbase + OFF_CNT + 8 * S, (tid & 31) == 0 ? 1u : 0u);
     uint32_t a[16];
     gray4(q0.x, q0.y, q0.z, a[0], a[1], a[2], a[3]);
     gray4(q0.w, q1.x, q1.y, a[4], a[5], a[6], a[7]);
@@ -199,6 +209,9 @@ __device__ __forceinline__ uint32_t load_row(const Band &B, int q, uint32_t pari
     // neighbour pixels x-1 and x+16 (REFLECT_101 at the frame edges: x=-1 -> 1, x=W -> W-2)
     uint32_t aL = __dp2a_hi(C_GR, wl, __dp2a_lo(C_0B, wl, RND));
     uint32_t aR = __dp2a_hi(C_R0, wr, __dp2a_lo(C_BG, wr, RND));
+    // every lane of this warp has its bytes in registers: count the warp off the stage (result used much later)
+    __syncwarp();
+    const uint32_t ticket = stage_arrive(B.sbase + OFF_CNT + 8 * S, (tid & 31) == 0 ? 1u : 0u, aL ^ aR);
     aL = first ? a[1] : aL;
     aR = last ? a[14] : aR;
 #pragma unroll
@@ -207,29 +220,43 @@ __device__ __forceinline__ uint32_t load_row(const Band &B, int q, uint32_t pari
         R.O[g] = __byte_perm(a[4 * g + 1], a[4 * g + 3], 0x7632);
     }
     R.LR = __byte_perm(aL, aR, 0x7632);
-    // thumbnail tap row?  info: bit0 tap, bit1 second row of its pair, bits 2-3 pair slot, bit4 wait for the slot, bit5 its parity
+    // thumbnail tap row?  info: bit0 tap, bit1 second row of its pair, bits 2-13 vertical weight, bits 16-24 thumbnail row
     uint32_t info;
-    asm volatile("ld.shared.u8 %0, [%1];" : "=r"(info) : "r"(B.sbase + OFF_INFO + q));
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(info) : "r"(B.sbase + OFF_INFO + 4 * q));
     if (info & 1u) {
-        const uint32_t slot = (info >> 2) & 3u;
-        if (info & 16u) mbar_wait(B.sbase + OFF_REMPTY + 8 * slot, (info >> 5) & 1u);
         uint4 gw;
         gw.x = __byte_perm(R.E[0], R.O[0], 0x6240); gw.y = __byte_perm(R.E[1], R.O[1], 0x6240);
         gw.z = __byte_perm(R.E[2], R.O[2], 0x6240); gw.w = __byte_perm(R.E[3], R.O[3], 0x6240);
-        if (active) *(uint4 *)(B.ring + (2 * slot + ((info >> 1) & 1u)) * B.W + 16 * tid) = gw;
+        asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(B.slot), "r"(gw.x), "r"(gw.y), "r"(gw.z), "r"(gw.w) : "memory");
+        asm volatile("st.shared.u8 [%0+16], %1;" ::"r"(B.slot), "r"(aR >> 16) : "memory");
+        const uint32_t bw = (info >> 2) & 0xfffu;
+        uint32_t u[JT];
+#pragma unroll
+        for (int k = 0; k < JT; k++) {
+            uint32_t g0, g1;
+            asm volatile("ld.shared.u8 %0, [%1];" : "=r"(g0) : "r"(T.addr[k]) : "memory");
+            asm volatile("ld.shared.u8 %0, [%1+1];" : "=r"(g1) : "r"(T.addr[k]) : "memory");
+            const uint32_t Sx = g0 * T.a0[k] + g1 * T.a1[k];
+            u[k] = (bw * (Sx >> 4)) >> 16;
+        }
         if (info & 2u) {
-            __syncwarp();
-            if ((tid & 31) == 0) mbar_arrive(B.sbase + OFF_RFULL + 8 * slot);
+            uint8_t *dst = T.dst + (size_t)(info >> 16) * AVD_T;
+#pragma unroll
+            for (int k = 0; k < JT; k++)
+                if (k < T.ntx) dst[k] = (uint8_t)((T.u0[k] + u[k] + 2u) >> 2);
+        } else {
+#pragma unroll
+            for (int k = 0; k < JT; k++) T.u0[k] = u[k];
         }
     }
     return ticket;
 }
 
 // the warp that arrived last at stage S refills it with sequence row q + NRS
-template <int S>
-__device__ __forceinline__ void release_finish(const Band &B, int q, uint32_t ticket, int tid)
+template <int POS>
+__device__ __forceinline__ void release_finish(const Band &B, int q, int grp, uint32_t ticket)
 {
-    if (ticket == 1u && q + NRS < B.nseq) issue_row(B, q + NRS, S);
+    if (ticket == 1u && q + NRS < B.nseq) issue_row(B, q + NRS, 3 * grp + POS);
 }
 
 __device__ __forceinline__ uint8_t sat_rne(float v)
@@ -272,12 +299,12 @@ __device__ float area_cell_exact(const uint8_t *src, size_t pitch, const ShapeTa
     return sum;
 }
 
-template <int MAXT, int MINB>
+template <int MAXT, int MINB, int JT>
 __global__ void __launch_bounds__(MAXT, MINB) k1_fused_kernel(K1Params P)
 {
     extern __shared__ __align__(128) uint8_t smem[];
     const int tid = threadIdx.x, lane = tid & 31;
-    const int nmain = blockDim.x - 32, nw = nmain >> 5;
+    const int nthr = blockDim.x, nw = nthr >> 5;
     const int b = blockIdx.x, f = blockIdx.y;
     const ShapeTables *__restrict__ tab = P.tab;
     const int H = P.H, W = P.W;
@@ -285,11 +312,11 @@ __global__ void __launch_bounds__(MAXT, MINB) k1_fused_kernel(K1Params P)
     const int n = own1 - own0, nseq = n + 2;
     const int ty_begin = tab->thumb_row_begin[b], nty = tab->thumb_row_begin[b + 1] - ty_begin;
     const uint32_t sbase = smem_u32(smem);
-    uint8_t *ring = smem + HDR + NRS * P.row_bytes;
     const uint8_t *frame = P.bgr + (size_t)f * P.fstride;
 
     Band B;
-    B.sbase = sbase; B.stage = sbase + HDR; B.ring = ring; B.row_bytes = P.row_bytes; B.W = W; B.H = H; B.own0 = own0;
+    B.sbase = sbase; B.stage = sbase + HDR; B.slot = sbase + HDR + NRS * P.row_bytes + 64 + SLOT * tid;
+    B.row_bytes = P.row_bytes; B.W = W; B.H = H; B.own0 = own0;
     B.nseq = nseq; B.nw = nw; B.frame = frame; B.pitch = P.pitch;
     asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(B.pol_stream));
     asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(B.pol_keep));
@@ -299,51 +326,39 @@ __global__ void __launch_bounds__(MAXT, MINB) k1_fused_kernel(K1Params P)
             mbar_init(sbase + OFF_FULL + 8 * s, 1);
             mbar_init(sbase + OFF_CNT + 8 * s, nw);
         }
-        for (int p = 0; p < RP; p++) { mbar_init(sbase + OFF_RFULL + 8 * p, nw); mbar_init(sbase + OFF_REMPTY + 8 * p, 1); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         for (int q = 0; q < NRS; q++) issue_row(B, q, q);
     }
     if (tid < 32) ((int *)(smem + OFF_CELL))[tid] = 0;
-
-    if (tid >= nmain) {
-        // ================= thumb warp =================
-        uint8_t *info = smem + OFF_INFO;
-        for (int q = lane; q < nseq; q += 32) info[q] = 0;
-        __syncwarp();
-        for (int j = lane; j < nty; j += 32) {
-            const int q0 = tab->ly[ty_begin + j].i0 - (own0 - 1);
-            const int slot = j % RP, rnd = j / RP;
-            info[q0] = (uint8_t)(1 | (slot << 2) | (rnd > 0 ? 16 : 0) | (((rnd - 1) & 1) << 5));
-            info[q0 + 1] = (uint8_t)(1 | 2 | (slot << 2));
-        }
-        int x0[NTX], a0[NTX], a1[NTX];
-#pragma unroll
-        for (int k = 0; k < NTX; k++) {
-            const LinTap t = tab->lx[lane + 32 * k];
-            x0[k] = t.i0; a0[k] = t.a0; a1[k] = t.a1;
-        }
+    // tap rows of this band's thumbnail rows (top tap row owned by the band, bottom tap = the row below it)
+    {
+        uint32_t *info = (uint32_t *)(smem + OFF_INFO);
+        for (int q = tid; q < nseq; q += nthr) info[q] = 0;
         __syncthreads();
-        for (int j = 0; j < nty; j++) {
-            const int slot = j % RP;
+        for (int j = tid; j < nty; j += nthr) {
             const LinTap vy = tab->ly[ty_begin + j];
-            mbar_wait(sbase + OFF_RFULL + 8 * slot, (uint32_t)((j / RP) & 1));
-            const uint8_t *p0 = ring + (2 * slot) * W, *p1 = p0 + W;
-            uint8_t *dst = P.thumbs + ((size_t)f * AVD_T + (ty_begin + j)) * AVD_T + lane;
-#pragma unroll
-            for (int k = 0; k < NTX; k++) {
-                const int S0 = p0[x0[k]] * a0[k] + p0[x0[k] + 1] * a1[k];
-                const int S1 = p1[x0[k]] * a0[k] + p1[x0[k] + 1] * a1[k];
-                dst[32 * k] = (uint8_t)((((vy.a0 * (S0 >> 4)) >> 16) + ((vy.a1 * (S1 >> 4)) >> 16) + 2) >> 2);
-            }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(sbase + OFF_REMPTY + 8 * slot);
+            const int q0 = vy.i0 - (own0 - 1);
+            info[q0] = 1u | ((uint32_t)vy.a0 << 2) | ((uint32_t)(ty_begin + j) << 16);
+            info[q0 + 1] = 3u | ((uint32_t)vy.a1 << 2) | ((uint32_t)(ty_begin + j) << 16);
         }
-        return;
     }
-
-    // ================= main warps =================
+    // this thread's thumbnail columns
+    Thumb<JT> T;
+    {
+        const int tx0 = tab->strip_tx0[tid];
+        T.ntx = 16 * tid < W ? tab->strip_ntx[tid] : 0;
+        T.dst = P.thumbs + (size_t)f * AVD_T * AVD_T + tx0;
+#pragma unroll
+        for (int k = 0; k < JT; k++) {
+            const LinTap t = tab->lx[min(tx0 + k, AVD_T - 1)];
+            const bool ok = k < T.ntx;
+            T.addr[k] = B.slot + (ok ? (uint32_t)(t.i0 - 16 * tid) : 0u);
+            T.a0[k] = (uint32_t)t.a0; T.a1[k] = (uint32_t)t.a1; T.u0[k] = 0;
+        }
+    }
     __syncthreads();
+
     const bool active = 16 * tid < W, first = tid == 0, last = 16 * tid + 16 == W;
     RowSet R0, R1, R2;
     Acc A;
@@ -360,10 +375,10 @@ __global__ void __launch_bounds__(MAXT, MINB) k1_fused_kernel(K1Params P)
     const int wh = 32 * own0 - b * H;                     // weight of the head row (sequence row 0), 1/32 units
     const int wt = (b + 1) * H - 32 * (own1 - 1);         // weight of the last owned row, 1/32 units (32 = full)
 
-    uint32_t t0 = load_row<0>(B, 0, 0u, tid, active, first, last, R0);
-    release_finish<0>(B, 0, t0, tid);
-    uint32_t t1 = load_row<1>(B, 1, 0u, tid, active, first, last, R1);
-    release_finish<1>(B, 1, t1, tid);
+    uint32_t t0 = load_row<0>(B, 0, 0, 0u, tid, first, last, R0, T);
+    release_finish<0>(B, 0, 0, t0);
+    uint32_t t1 = load_row<1>(B, 1, 0, 0u, tid, first, last, R1, T);
+    release_finish<1>(B, 1, 0, t1);
     int tv = (int)row_sum(R0) - (int)row_sum(R1);         // vertical part of sum L telescopes to 4 rows per band
     int mcA = 0, mcB = 0;                                  // cell sums in 1/32 units
     if (wh > 0) {
@@ -384,21 +399,22 @@ __global__ void __launch_bounds__(MAXT, MINB) k1_fused_kernel(K1Params P)
     };
 
     uint32_t par = 0;
-    int q = 2;
+    int q = 2, grp = 0;
     while (true) {
-        uint32_t tk = load_row<2>(B, q, par, tid, active, first, last, R2);
+        uint32_t tk = load_row<2>(B, q, grp, par, tid, first, last, R2, T);
         lap_step(R0, R1, R2, A);
-        release_finish<2>(B, q, tk, tid);
+        release_finish<2>(B, q, grp, tk);
         if (q == nseq - 1) { band_end(R1, R2); break; }
-        q++; par ^= 1u;
-        tk = load_row<0>(B, q, par, tid, active, first, last, R0);
+        q++;
+        if (++grp == NGRP) { grp = 0; par ^= 1u; }
+        tk = load_row<0>(B, q, grp, par, tid, first, last, R0, T);
         lap_step(R1, R2, R0, A);
-        release_finish<0>(B, q, tk, tid);
+        release_finish<0>(B, q, grp, tk);
         if (q == nseq - 1) { band_end(R2, R0); break; }
         q++;
-        tk = load_row<1>(B, q, par, tid, active, first, last, R1);
+        tk = load_row<1>(B, q, grp, par, tid, first, last, R1, T);
         lap_step(R2, R0, R1, A);
-        release_finish<1>(B, q, tk, tid);
+        release_finish<1>(B, q, grp, tk);
         if (q == nseq - 1) { band_end(R0, R1); break; }
         q++;
     }
@@ -419,7 +435,7 @@ __global__ void __launch_bounds__(MAXT, MINB) k1_fused_kernel(K1Params P)
     for (int o = 16; o; o >>= 1) { sumL += __shfl_down_sync(0xffffffffu, sumL, o); sq += __shfl_down_sync(0xffffffffu, sq, o); }
     unsigned long long *red = (unsigned long long *)(smem + OFF_RED);
     if (lane == 0) { red[tid >> 5] = (unsigned long long)sumL; red[8 + (tid >> 5)] = sq; }
-    main_sync(nmain);
+    __syncthreads();
     uint32_t *misc = (uint32_t *)(smem + OFF_MISC);
     if (tid < 32) {
         long long s1 = tid < nw ? (long long)red[tid] : 0;
@@ -448,7 +464,7 @@ __global__ void __launch_bounds__(MAXT, MINB) k1_fused_kernel(K1Params P)
         const uint32_t mask = __ballot_sync(0xffffffffu, close);
         if (tid == 0) misc[0] = mask;
     }
-    main_sync(nmain);
+    __syncthreads();
     uint32_t mask = misc[0];
     while (mask) {                                      // rare: cells too close to a rounding boundary
         const int dx = __ffs(mask) - 1;
@@ -461,14 +477,18 @@ __global__ void __launch_bounds__(MAXT, MINB) k1_fused_kernel(K1Params P)
 
 }  // namespace
 
-static size_t k1_smem_bytes(int W) { return HDR + (size_t)NRS * 3 * W + (size_t)2 * RP * W + 64; }
+static size_t k1_smem_bytes(int W)
+{
+    const int nthr = (W / 16 + 31) / 32 * 32;
+    return HDR + (size_t)NRS * 3 * W + 64 + (size_t)SLOT * nthr + 64;
+}
 
 bool k1_fused_supported(int H, int W, size_t pitch, size_t fstride, const void *base, const ShapeTables *htab)
 {
-    if (W % 64 != 0 || W < 640 || W > 4096 || H < 640 || H > 4096 || htab->thumb_2x2) return false;
+    if (W % 64 != 0 || W < 1280 || W > 4096 || H < 640 || H > 4096 || htab->thumb_2x2) return false;
     if (pitch % 16 != 0 || fstride % 16 != 0 || ((uintptr_t)base % 16) != 0) return false;
-    if (k1_smem_bytes(W) > 227 * 1024) return false;
-    // the thumb warp assumes plain two-tap decimation: taps (i, i+1), every tap row used by one thumbnail row
+    if (k1_smem_bytes(W) > 227 * 1024 || htab->strip_ntx_max > 4) return false;
+    // plain two-tap decimation: taps (i, i+1), every tap row used by exactly one thumbnail row
     for (int i = 0; i < AVD_T; i++) {
         if (htab->lx[i].i1 != htab->lx[i].i0 + 1 || htab->ly[i].i1 != htab->ly[i].i0 + 1) return false;
         if (i > 0 && htab->ly[i].i0 < htab->ly[i - 1].i0 + 2) return false;
@@ -476,31 +496,38 @@ bool k1_fused_supported(int H, int W, size_t pitch, size_t fstride, const void *
     return true;
 }
 
-int k1_fused(avd_ctx *ctx, const uint8_t *d_bgr, int n, int H, int W, size_t pitch, size_t fstride,
-             const ShapeTables *tab, const ShapeTables *htab, avd_sample_rec *d_rec, uint8_t *d_thumbs,
-             uint8_t *d_area32, cudaStream_t st)
+template <int MAXT, int MINB, int JT>
+static int k1_launch(avd_ctx *ctx, const K1Params &P, int n, size_t smem, int threads, cudaStream_t st)
 {
-    (void)htab;
-    K1Params P{};
-    P.bgr = d_bgr; P.pitch = pitch; P.fstride = fstride; P.H = H; P.W = W; P.row_bytes = 3 * W;
-    P.tab = tab; P.rec = d_rec; P.thumbs = d_thumbs; P.area32 = d_area32;
-    const size_t smem = k1_smem_bytes(W);
-    const int nw = (W / 16 + 31) / 32;
-    const int threads = (nw + 1) * 32;
-    const bool narrow = nw <= 4;                                     // <= 2048 px wide
-    static size_t smem_set[2] = {0, 0};
-    if (smem > smem_set[narrow]) {
-        if (narrow) AVD_CUDA(ctx, cudaFuncSetAttribute(k1_fused_kernel<160, K1_MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        else AVD_CUDA(ctx, cudaFuncSetAttribute(k1_fused_kernel<288, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        smem_set[narrow] = smem;
+    static size_t smem_set = 0;
+    if (smem > smem_set) {
+        AVD_CUDA(ctx, cudaFuncSetAttribute(k1_fused_kernel<MAXT, MINB, JT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        smem_set = smem;
     }
     for (int f0 = 0; f0 < n; f0 += 65535) {                          // grid.y limit
         int nb = n - f0 < 65535 ? n - f0 : 65535;
         K1Params Q = P;
-        Q.bgr = d_bgr + (size_t)f0 * fstride; Q.rec = d_rec + f0;
-        Q.thumbs = d_thumbs + (size_t)f0 * AVD_T * AVD_T; Q.area32 = d_area32 + (size_t)f0 * 1024;
-        if (narrow) AVD_LAUNCH(ctx, "k1_fused", st, (k1_fused_kernel<160, K1_MINB><<<dim3(AVD_D, nb), threads, smem, st>>>(Q)));
-        else AVD_LAUNCH(ctx, "k1_fused", st, (k1_fused_kernel<288, 2><<<dim3(AVD_D, nb), threads, smem, st>>>(Q)));
+        Q.bgr = P.bgr + (size_t)f0 * P.fstride; Q.rec = P.rec + f0;
+        Q.thumbs = P.thumbs + (size_t)f0 * AVD_T * AVD_T; Q.area32 = P.area32 + (size_t)f0 * 1024;
+        AVD_LAUNCH(ctx, "k1_fused", st, (k1_fused_kernel<MAXT, MINB, JT><<<dim3(AVD_D, nb), threads, smem, st>>>(Q)));
     }
     return AVD_OK;
+}
+
+int k1_fused(avd_ctx *ctx, const uint8_t *d_bgr, int n, int H, int W, size_t pitch, size_t fstride,
+             const ShapeTables *tab, const ShapeTables *htab, avd_sample_rec *d_rec, uint8_t *d_thumbs,
+             uint8_t *d_area32, cudaStream_t st)
+{
+    K1Params P{};
+    P.bgr = d_bgr; P.pitch = pitch; P.fstride = fstride; P.H = H; P.W = W; P.row_bytes = 3 * W;
+    P.tab = tab; P.rec = d_rec; P.thumbs = d_thumbs; P.area32 = d_area32;
+    const size_t smem = k1_smem_bytes(W);
+    const int threads = (W / 16 + 31) / 32 * 32;
+    const int jt = htab->strip_ntx_max;
+    if (threads <= 128) {                                            // <= 2048 px wide
+        if (jt <= 3) return k1_launch<128, K1_MINB, 3>(ctx, P, n, smem, threads, st);
+        return k1_launch<128, K1_MINB, 4>(ctx, P, n, smem, threads, st);
+    }
+    if (jt <= 2) return k1_launch<256, 2, 2>(ctx, P, n, smem, threads, st);
+    return k1_launch<256, 2, 3>(ctx, P, n, smem, threads, st);
 }

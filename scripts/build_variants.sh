@@ -7,7 +7,6 @@ mkdir -p variants
 while [ $# -gt 1 ]; do
   name=$1; flags=$2; shift 2
   $NV $flags -c k1_fused.cu -o variants/k1_fused_$name.o
-  $NV $flags -c k2_flow.cu -o variants/k2_flow_$name.o
-  $NV -shared -o variants/libavd_$name.so avd_api.o k1_generic.o variants/k1_fused_$name.o variants/k2_flow_$name.o
+  $NV -shared -o variants/libavd_$name.so avd_api.o k1_generic.o k1_banded.o variants/k1_fused_$name.o k2_flow.o
   echo built $name "($flags)"
 done
