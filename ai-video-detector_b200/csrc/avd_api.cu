@@ -4,6 +4,7 @@
 #include <string.h>
 #include <stdio.h>
 #include <new>
+#include <memory>
 #include <vector>
 
 static_assert(sizeof(avd_sample_rec) == 160, "record layout is part of the ABI");
@@ -63,7 +64,8 @@ int avd_get_tables(avd_ctx *ctx, int H, int W, const ShapeTables **dev, const Sh
     auto key = std::make_pair(H, W);
     auto it = ctx->tables.find(key);
     if (it == ctx->tables.end()) {
-        ShapeTables t{};
+        std::unique_ptr<ShapeTables> tp(new ShapeTables());   // 21 KB, value-initialised: keep it off the stack
+        ShapeTables &t = *tp;
         build_area_cells(W, AVD_D, t.ax);
         build_area_cells(H, AVD_D, t.ay);
         build_lin_taps(W, AVD_T, t.lx, false);
@@ -90,6 +92,16 @@ int avd_get_tables(avd_ctx *ctx, int H, int W, const ShapeTables **dev, const Sh
             while (tx + cnt < AVD_T && t.lx[tx + cnt].i0 < 16 * s + 16) cnt++;
             t.strip_tx0[s] = (uint16_t)tx; t.strip_ntx[s] = (uint8_t)(cnt > 255 ? 255 : cnt);
             if (16 * s < W && cnt > t.strip_ntx_max) t.strip_ntx_max = cnt;
+        }
+        if (H <= 4096) {
+            bool single_role = true;
+            for (int y = 0; y < AVD_T && single_role; y++) {
+                const LinTap &v = t.ly[y];
+                if (v.i1 != v.i0 + 1 || t.rowinfo[v.i0] || t.rowinfo[v.i1]) { single_role = false; break; }
+                t.rowinfo[v.i0] = 1u | ((uint32_t)v.a0 << 2) | ((uint32_t)y << 16);
+                t.rowinfo[v.i1] = 3u | ((uint32_t)v.a1 << 2) | ((uint32_t)y << 16);
+            }
+            if (!single_role) memset(t.rowinfo, 0, sizeof t.rowinfo);
         }
         ShapeTables *d = nullptr;
         AVD_CUDA(ctx, cudaMalloc(&d, sizeof(ShapeTables)));
@@ -181,7 +193,7 @@ void avd_destroy(avd_ctx *ctx)
     cudaDeviceSynchronize();
     for (auto &kv : ctx->tables) cudaFree(kv.second);
     cudaFree(ctx->gray); cudaFree(ctx->area_rows); cudaFree(ctx->k2_ws); cudaFree(ctx->ring);
-    cudaFree(ctx->thumbs); cudaFree(ctx->recs); cudaFree(ctx->area32);
+    cudaFree(ctx->thumbs); cudaFree(ctx->recs); cudaFree(ctx->area32); cudaFree(ctx->areaflag);
     for (int i = 0; i < 4; i++) { cudaEventDestroy(ctx->ev_copied[i]); cudaEventDestroy(ctx->ev_free[i]); }
     cudaStreamDestroy(ctx->compute); cudaStreamDestroy(ctx->copy);
     cudaGetLastError();
@@ -281,14 +293,18 @@ int avd_frames_features(avd_ctx *ctx, const uint8_t *d_bgr, int n, int H, int W,
         d_area32 = ctx->area32;
     }
     if ((rc = k1_rec_init(ctx, d_rec, n, st))) return rc;
-    if (ctx->k1_mode == 0 && k1_fused_supported(H, W, row_pitch, frame_stride, d_bgr, htab))
-        rc = k1_fused(ctx, d_bgr, n, H, W, row_pitch, frame_stride, tab, htab, d_rec, d_thumbs, d_area32, st);
+    K1FixArgs fix{d_bgr, row_pitch, frame_stride, tab, nullptr};
+    if (ctx->k1_mode == 0 && k1_fused_supported(H, W, row_pitch, frame_stride, d_bgr, htab)) {
+        if ((rc = avd_ensure(ctx, (void **)&ctx->areaflag, &ctx->areaflag_cap, (size_t)n * 1024))) return rc;
+        fix.flags = ctx->areaflag;
+        rc = k1_fused(ctx, d_bgr, n, H, W, row_pitch, frame_stride, tab, htab, d_rec, d_thumbs, d_area32, ctx->areaflag, st);
+    }
     else if ((ctx->k1_mode == 0 || ctx->k1_mode == 2) && k1_banded_supported(H, W, row_pitch, frame_stride, d_bgr))
         rc = k1_banded(ctx, d_bgr, n, H, W, row_pitch, frame_stride, tab, htab, d_rec, d_thumbs, d_area32, st);
     else
         rc = k1_generic(ctx, d_bgr, n, H, W, row_pitch, frame_stride, tab, htab, d_rec, d_thumbs, d_area32, st);
     if (rc) return rc;
-    return k1_hash_finalize(ctx, d_area32, n, d_prev_hash, d_rec, st);
+    return k1_hash_finalize(ctx, d_area32, n, d_prev_hash, d_rec, fix.flags ? &fix : nullptr, st);
 }
 
 int avd_flow_stats(avd_ctx *ctx, const uint8_t *d_thumbs, int n, const uint8_t *d_prev_thumb,

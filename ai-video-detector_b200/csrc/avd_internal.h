@@ -40,6 +40,9 @@ struct ShapeTables {
     uint16_t strip_tx0[256];
     uint8_t strip_ntx[256];
     int strip_ntx_max;
+    // streaming kernel: role of source row r as a thumbnail tap row (0 = none): bit0 tap, bit1 bottom tap of its
+    // pair, bits 2-13 vertical weight, bits 16-24 thumbnail row.  Filled only when every row has at most one role.
+    uint32_t rowinfo[4096];
 };
 
 struct avd_ctx {
@@ -62,6 +65,7 @@ struct avd_ctx {
     uint8_t *thumbs = nullptr; size_t thumbs_cap = 0;
     avd_sample_rec *recs = nullptr; size_t recs_cap = 0;
     uint8_t *area32 = nullptr; size_t area32_cap = 0;
+    uint8_t *areaflag = nullptr; size_t areaflag_cap = 0;
     // optional per-kernel timing (avd_profile_enable): CUDA events around every launch, on its stream
     bool profiling = false;
     struct ProfRec { const char *name; cudaEvent_t a, b; };
@@ -110,8 +114,10 @@ int k1_generic(avd_ctx *ctx, const uint8_t *d_bgr, int n, int H, int W, size_t p
                const ShapeTables *tab, const ShapeTables *htab, avd_sample_rec *d_rec, uint8_t *d_thumbs,
                uint8_t *d_area32, cudaStream_t st);
 int k1_gray_only(avd_ctx *ctx, const uint8_t *d_bgr, int H, int W, size_t pitch, uint8_t *d_gray, cudaStream_t st);
-int k1_hash_finalize(avd_ctx *ctx, const uint8_t *d_area32, int n, const uint32_t *d_prev_hash,
-                     avd_sample_rec *d_rec, cudaStream_t st);
+// d_areaflag != NULL: cells flagged by the streaming kernel are first recomputed from the frames (exact float32 order)
+struct K1FixArgs { const uint8_t *bgr; size_t pitch, fstride; const ShapeTables *tab; const uint8_t *flags; };
+int k1_hash_finalize(avd_ctx *ctx, uint8_t *d_area32, int n, const uint32_t *d_prev_hash,
+                     avd_sample_rec *d_rec, const K1FixArgs *fix, cudaStream_t st);
 // k1_fused.cu (streaming kernel: W % 64 == 0, 640 <= W <= 4096, 640 <= H <= 4096) and k1_banded.cu (W % 16 == 0)
 bool k1_fused_supported(int H, int W, size_t pitch, size_t fstride, const void *base, const ShapeTables *htab);
 bool k1_banded_supported(int H, int W, size_t pitch, size_t fstride, const void *base);
@@ -120,7 +126,7 @@ int k1_banded(avd_ctx *ctx, const uint8_t *d_bgr, int n, int H, int W, size_t pi
               uint8_t *d_area32, cudaStream_t st);
 int k1_fused(avd_ctx *ctx, const uint8_t *d_bgr, int n, int H, int W, size_t pitch, size_t fstride,
              const ShapeTables *tab, const ShapeTables *htab, avd_sample_rec *d_rec, uint8_t *d_thumbs,
-             uint8_t *d_area32, cudaStream_t st);
+             uint8_t *d_area32, uint8_t *d_areaflag, cudaStream_t st);
 // k2_flow.cu
 int k2_flow(avd_ctx *ctx, const uint8_t *d_prev, const uint8_t *d_next, size_t prev_stride, size_t next_stride,
             int n_pairs, bool shared_chain, avd_sample_rec *d_rec_first, float *d_flow_out, cudaStream_t st);

@@ -27,14 +27,36 @@
 // rounded to u8 and only that byte is observable.  The kernel computes the exact rational cell mean from integer
 // sums; float32 evaluation in the library's order differs from it by at most (nx+ny+4) * 2^-24 relative
 // (standard forward error bound of recursive summation, nx/ny = taps per cell), so whenever the exact mean is
-// farther than twice that bound from a rounding boundary k+0.5 the library's byte is round(mean).  The few cells
-// (~0.5 %) that are closer are recomputed at the end of the band in the library's exact float32 order.
+// farther than that bound (taken with a 17/16 margin) from a rounding boundary k+0.5 the library's byte is
+// round(mean).  The few cells (~0.2 %) that are closer are flagged and recomputed in the library's exact float32
+// order by the hash kernel that follows (k1_generic.cu), off this kernel's critical path.
 #include "avd_internal.h"
 
 namespace {
 
 #ifndef K1_NRS
 #define K1_NRS 6
+#endif
+#ifndef K1_OPAQUE
+#define K1_OPAQUE 1
+#endif
+#ifndef K1_OPAQUE_BASE
+#define K1_OPAQUE_BASE 1
+#endif
+#ifndef K1_NOTHUMB
+#define K1_NOTHUMB 0
+#endif
+#ifndef K1_NOFIX
+#define K1_NOFIX 0
+#endif
+#ifndef K1_ISSUE_INLINE
+#define K1_ISSUE_INLINE __forceinline__
+#endif
+#ifndef K1_BANDPAR
+#define K1_BANDPAR 0
+#endif
+#ifndef K1_STUB
+#define K1_STUB 0
 #endif
 #ifndef K1_MINB
 #define K1_MINB 4
@@ -46,7 +68,7 @@ constexpr int MAXQ = 132;             // rows a band can load (H/32 + 3, H <= 40
 constexpr int SLOT = 48;              // bytes of a thread's private gray slot (48: conflict-free 128-bit stores)
 
 // shared-memory header (bytes)
-constexpr int OFF_FULL = 0, OFF_CNT = 64, OFF_MISC = 192, OFF_CELL = 256, OFF_RED = 384, OFF_INFO = 512, HDR = 1040;
+constexpr int OFF_FULL = 0, OFF_CNT = 64, OFF_PAR = 128, OFF_MISC = 192, OFF_CELL = 256, OFF_RED = 384, OFF_INFO = 512, HDR = 1040;
 static_assert(OFF_INFO + 4 * MAXQ <= HDR, "header layout");
 
 struct K1Params {
@@ -55,7 +77,7 @@ struct K1Params {
     int H, W, row_bytes;
     const ShapeTables *tab;
     avd_sample_rec *rec;
-    uint8_t *thumbs, *area32;
+    uint8_t *thumbs, *area32, *areaflag;
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -80,6 +102,7 @@ __device__ __noinline__ void mbar_wait_slow(uint32_t bar, uint32_t parity)
 {
     // try_wait suspends the thread in hardware for up to the hinted time, so this loop turns over rarely;
     // a lost refill must fail loudly instead of hanging the GPU
+#pragma unroll 1
     for (int it = 0; it < (1 << 22); it++) {
         uint32_t ok;
         asm volatile("{\n.reg .pred P1;\nmbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2, %3;\nselp.u32 %0, 1, 0, P1;\n}"
@@ -88,11 +111,13 @@ __device__ __noinline__ void mbar_wait_slow(uint32_t bar, uint32_t parity)
     }
     __trap();
 }
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
+// Non-blocking probe (test_wait, not try_wait: a failing try_wait suspends the warp), issued early so that its latency
+// hides behind the previous row's arithmetic; the branch on the result comes a row later.
+__device__ __forceinline__ uint32_t mbar_try(uint32_t bar, uint32_t parity)
 {
     uint32_t ok;
-    asm volatile("{\n.reg .pred P1;\nmbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\nselp.u32 %0, 1, 0, P1;\n}" : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
-    if (!ok) mbar_wait_slow(bar, parity);
+    asm volatile("{\n.reg .pred P1;\nmbarrier.test_wait.parity.shared::cta.b64 P1, [%1], %2;\nselp.u32 %0, 1, 0, P1;\n}" : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    return ok;
 }
 // lane 0 of a warp counts the warp off a stage; returns 1 in the lane that arrived last (pending count before its arrival)
 // `dep` is a value computed from the last bytes loaded from the stage: the arrival cannot be issued before they landed
@@ -110,13 +135,29 @@ constexpr uint32_t C_BG = WB | (WG << 16), C_R0 = WR, C_0B = WB << 16, C_GR = WG
 constexpr uint32_t RND = 32768u;
 constexpr uint32_t KBIAS = 1020u | (1020u << 16);
 
+// IDP takes its weights from registers: keep them resident (loaded once through an opaque move) instead of letting
+// the compiler rematerialise five constants on every row
+struct GrayK {
+    uint32_t bg, r0, ob, gr, rnd;
+    __device__ __forceinline__ void load()
+    {
+#if !K1_OPAQUE
+        bg = C_BG; r0 = C_R0; ob = C_0B; gr = C_GR; rnd = RND;
+        return;
+#endif
+        asm volatile("mov.u32 %0, %1;" : "=r"(bg) : "n"(C_BG)); asm volatile("mov.u32 %0, %1;" : "=r"(r0) : "n"(C_R0));
+        asm volatile("mov.u32 %0, %1;" : "=r"(ob) : "n"(C_0B)); asm volatile("mov.u32 %0, %1;" : "=r"(gr) : "n"(C_GR));
+        asm volatile("mov.u32 %0, %1;" : "=r"(rnd) : "n"(RND));
+    }
+};
+
 // gray accumulators of 4 consecutive pixels held in 3 consecutive words
-__device__ __forceinline__ void gray4(uint32_t w0, uint32_t w1, uint32_t w2, uint32_t &a0, uint32_t &a1, uint32_t &a2, uint32_t &a3)
+__device__ __forceinline__ void gray4(const GrayK &K, uint32_t w0, uint32_t w1, uint32_t w2, uint32_t &a0, uint32_t &a1, uint32_t &a2, uint32_t &a3)
 {
-    a0 = __dp2a_hi(C_R0, w0, __dp2a_lo(C_BG, w0, RND));      // B=w0.0 G=w0.1 R=w0.2
-    a1 = __dp2a_lo(C_GR, w1, __dp2a_hi(C_0B, w0, RND));      // B=w0.3 G=w1.0 R=w1.1
-    a2 = __dp2a_lo(C_R0, w2, __dp2a_hi(C_BG, w1, RND));      // B=w1.2 G=w1.3 R=w2.0
-    a3 = __dp2a_hi(C_GR, w2, __dp2a_lo(C_0B, w2, RND));      // B=w2.1 G=w2.2 R=w2.3
+    a0 = __dp2a_hi(K.r0, w0, __dp2a_lo(K.bg, w0, K.rnd));      // B=w0.0 G=w0.1 R=w0.2
+    a1 = __dp2a_lo(K.gr, w1, __dp2a_hi(K.ob, w0, K.rnd));      // B=w0.3 G=w1.0 R=w1.1
+    a2 = __dp2a_lo(K.r0, w2, __dp2a_hi(K.bg, w1, K.rnd));      // B=w1.2 G=w1.3 R=w2.0
+    a3 = __dp2a_hi(K.gr, w2, __dp2a_lo(K.ob, w2, K.rnd));      // B=w2.1 G=w2.2 R=w2.3
 }
 
 // one gray row of a 16-pixel strip: E[g] = (p[4g], p[4g+2]), O[g] = (p[4g+1], p[4g+3]) in 16-bit lanes,
@@ -135,37 +176,122 @@ __device__ __forceinline__ uint32_t row_sum(const RowSet &R)
     return lanes_sum(R.E[0] + R.E[1] + R.E[2] + R.E[3] + R.O[0] + R.O[1] + R.O[2] + R.O[3]);
 }
 
-// Laplacian statistics of centre row C (rows above / below: U, D) and its INTER_AREA column sums
-__device__ __forceinline__ void lap_step(const RowSet &U, const RowSet &C, const RowSet &D, Acc &A)
-{
-#pragma unroll
-    for (int g = 0; g < 4; g++) {
-        // left neighbours of (p0,p2) are (pL,p1); right neighbours of (p1,p3) are (p2,pR)
-        const uint32_t el = g == 0 ? __byte_perm(C.LR, C.O[0], 0x5410) : __byte_perm(C.O[g - 1], C.O[g], 0x5432);
-        const uint32_t orr = g == 3 ? __byte_perm(C.E[3], C.LR, 0x7632) : __byte_perm(C.E[g], C.E[g + 1], 0x5432);
-        const uint32_t me = KBIAS - 4u * C.E[g], mo = KBIAS - 4u * C.O[g];
-        const uint32_t le = (el + C.O[g] + me) + U.E[g] + D.E[g];      // L+1020 of (p0,p2), each in [0,2040]
-        const uint32_t lo = (C.E[g] + orr + mo) + U.O[g] + D.O[g];     // L+1020 of (p1,p3)
-        const uint32_t pl = __byte_perm(le, lo, 0x6420), ph = __byte_perm(le, lo, 0x7531);
-        A.ll = __dp4a(pl, pl, A.ll);
-        A.hl = __dp4a(ph, pl, A.hl);
-        A.hh = __dp4a(ph, ph, A.hh);
-        A.cs[g] += C.E[g] + C.O[g];
-    }
-    A.aLR += C.LR; A.aE0 += C.E[0]; A.aO3 += C.O[3];
-}
-
 struct Band {
     uint32_t sbase;                       // shared address of the header
     uint32_t stage;                       // shared address of stage 0
     uint32_t slot;                        // shared address of this thread's private gray slot
-    int row_bytes, W, H, own0, nseq, nw;
+    int row_bytes, nseq;
+#if !K1_BANDPAR
+    int H, own0;
     const uint8_t *frame;
     size_t pitch;
     uint64_t pol_stream, pol_keep;
+#endif
+    GrayK K;
+    int todd;                             // pair-sum thumbnail: tap pairs start at odd offsets
 };
 
+// thumbnail columns owned by this thread (left tap inside its strip): shared address of the left tap byte in the
+// thread's slot, the two horizontal weights, the vertically weighted first tap row carried to the second
+template <int JT> struct Thumb {
+    uint32_t addr[JT], a0[JT], a1[JT], u0[JT];
+    int ntx;
+    uint8_t *dst;                          // &thumbs[frame][0][first column of this thread]
+};
+
+// ---- thumbnail, pair-sum form (W a multiple of 640: every horizontal tap pair has weights 1024/1024, so the
+// horizontal pass is 1024 * (p[x0] + p[x0+1]) and those pair sums already exist in 16-bit lanes: E+O holds the pairs
+// starting at even offsets, O+orr the pairs starting at odd offsets).  The four registers go to the thread's private
+// slot and each thumbnail column of the thread reads its lane back at its own (per-thread constant) offset.
+template <int JT>
+__device__ __forceinline__ void thumb_pairs_store(const Band &B, const uint32_t *X)
+{
+    asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(B.slot), "r"(X[0]), "r"(X[1]), "r"(X[2]), "r"(X[3]) : "memory");
+}
+template <int JT>
+__device__ __forceinline__ void thumb_pairs_finish(Thumb<JT> &T, uint32_t info)
+{
+    const uint32_t bw = (info >> 2) & 0xfffu;
+    uint32_t u[JT];
+#pragma unroll
+    for (int k = 0; k < JT; k++) {
+        uint32_t sum;
+        asm volatile("ld.shared.u16 %0, [%1];" : "=r"(sum) : "r"(T.addr[k]) : "memory");
+        u[k] = (bw * sum) >> 10;             // (bw * ((1024 * sum) >> 4)) >> 16
+    }
+    if (info & 2u) {
+        uint8_t *dst = T.dst + (size_t)(info >> 16) * AVD_T;
+#pragma unroll
+        for (int k = 0; k < JT; k++)
+            if (k < T.ntx) dst[k] = (uint8_t)((T.u0[k] + u[k] + 2u) >> 2);
+    } else {
+#pragma unroll
+        for (int k = 0; k < JT; k++) T.u0[k] = u[k];
+    }
+}
+
+// Laplacian statistics of centre row C (rows above / below: U, D), its INTER_AREA column sums and, in the pair-sum
+// form of the thumbnail, its thumbnail columns (infoC = thumbnail role of the centre row)
+template <int JT, bool PAIR>
+__device__ __forceinline__ void lap_step(const Band &B, const RowSet &U, const RowSet &C, const RowSet &D, Acc &A, Thumb<JT> &T, uint32_t infoC)
+{
+#if K1_STUB
+    A.ll += U.E[0] + C.E[1] + D.E[2] + C.E[3] + C.O[0] + C.LR;
+    return;
+#endif
+    uint32_t el[4], orr[4], Pp[4];
+#pragma unroll
+    for (int g = 0; g < 4; g++) {
+        // left neighbours of (p0,p2) are (pL,p1); right neighbours of (p1,p3) are (p2,pR)
+        el[g] = g == 0 ? __byte_perm(C.LR, C.O[0], 0x5410) : __byte_perm(C.O[g - 1], C.O[g], 0x5432);
+        orr[g] = g == 3 ? __byte_perm(C.E[3], C.LR, 0x7632) : __byte_perm(C.E[g], C.E[g + 1], 0x5432);
+        Pp[g] = C.E[g] + C.O[g];
+    }
+#if !K1_NOTHUMB
+    if (PAIR && (infoC & 1u)) {
+        if (B.todd) {
+            uint32_t Q[4];
+#pragma unroll
+            for (int g = 0; g < 4; g++) Q[g] = C.O[g] + orr[g];
+            thumb_pairs_store<JT>(B, Q);
+        } else {
+            thumb_pairs_store<JT>(B, Pp);
+        }
+    }
+#endif
+#pragma unroll
+    for (int g = 0; g < 4; g++) {
+        const uint32_t me = KBIAS - 4u * C.E[g], mo = KBIAS - 4u * C.O[g];
+        const uint32_t le = (el[g] + C.O[g] + me) + U.E[g] + D.E[g];      // L+1020 of (p0,p2), each in [0,2040]
+        const uint32_t lo = (C.E[g] + orr[g] + mo) + U.O[g] + D.O[g];     // L+1020 of (p1,p3)
+        const uint32_t pl = __byte_perm(le, lo, 0x6420), ph = __byte_perm(le, lo, 0x7531);
+        A.ll = __dp4a(pl, pl, A.ll);
+        A.hl = __dp4a(ph, pl, A.hl);
+        A.hh = __dp4a(ph, ph, A.hh);
+        A.cs[g] += Pp[g];
+    }
+    A.aLR += C.LR; A.aE0 += C.E[0]; A.aO3 += C.O[3];
+#if !K1_NOTHUMB
+    if (PAIR && (infoC & 1u)) thumb_pairs_finish<JT>(T, infoC);
+#endif
+}
+
+// What the out-of-line helpers (row refill, cell fix-up) need, kept in shared memory so that calling them costs the
+// hot loop no registers (they run in one lane / one warp, rarely).
+struct BandPar {
+    const uint8_t *frame;
+    unsigned long long pitch, pol_stream, pol_keep;
+    const ShapeTables *tab;
+    int row_bytes, own0, H, nseq;
+};
+static_assert(sizeof(BandPar) <= OFF_MISC - OFF_PAR, "header layout");
+__device__ __forceinline__ const BandPar *band_par(uint32_t sbase)
+{
+    return (const BandPar *)__cvta_shared_to_generic((size_t)(sbase + OFF_PAR));
+}
+
 // sequence row q of the band = source row own0-1+q, reflected at the frame edges (BORDER_REFLECT_101)
+#if !K1_BANDPAR
 __device__ __forceinline__ void issue_row(const Band &B, int q, int s)
 {
     int r = B.own0 - 1 + q;
@@ -176,23 +302,29 @@ __device__ __forceinline__ void issue_row(const Band &B, int q, int s)
     const bool shared_row = q < 2 || q >= B.nseq - 2;
     tma_load_1d(B.stage + s * B.row_bytes, B.frame + (size_t)r * B.pitch, (uint32_t)B.row_bytes, bar, shared_row ? B.pol_keep : B.pol_stream);
 }
-
-// thumbnail columns owned by this thread (left tap inside its strip): shared address of the left tap byte in the
-// thread's slot, the two horizontal weights, the vertically weighted first tap row carried to the second
-template <int JT> struct Thumb {
-    uint32_t addr[JT], a0[JT], a1[JT], u0[JT];
-    int ntx;
-    uint8_t *dst;                          // &thumbs[frame][0][first column of this thread]
-};
+#endif
+__device__ K1_ISSUE_INLINE void issue_row(uint32_t sbase, int q, int s)
+{
+    const BandPar *bp = band_par(sbase);
+    int r = bp->own0 - 1 + q;
+    r = r < 0 ? 1 : (r >= bp->H ? bp->H - 2 : r);
+    const uint32_t bar = sbase + OFF_FULL + 8 * s;   // s = 3 * group + position
+    mbar_expect_tx(bar, (uint32_t)bp->row_bytes);
+    // the two first and two last rows of a band are also read by the neighbouring bands: do not mark them evict-first
+    const bool shared_row = q < 2 || q >= bp->nseq - 2;
+    tma_load_1d(sbase + HDR + s * bp->row_bytes, bp->frame + (size_t)r * bp->pitch, (uint32_t)bp->row_bytes, bar,
+                shared_row ? bp->pol_keep : bp->pol_stream);
+}
 
 // Stage s holds sequence row q: convert this thread's strip to gray (row set R); on tap rows of the thumbnail also
 // advance this thread's thumbnail columns.  Returns 1 in lane 0 of the warp that was last to leave the stage
 // (passed on to release_finish).
-template <int POS, int JT>
-__device__ __forceinline__ uint32_t load_row(const Band &B, int q, int grp, uint32_t parity, int tid, bool first, bool last, RowSet &R, Thumb<JT> &T)
+template <int POS, int JT, bool PAIR>
+__device__ __forceinline__ uint32_t load_row(const Band &B, int q, int grp, uint32_t parity, uint32_t &ok, uint32_t nbar, uint32_t npar,
+                                             int tid, bool first, bool last, RowSet &R, Thumb<JT> &T)
 {
     const int S = 3 * grp + POS;
-    mbar_wait(B.sbase + OFF_FULL + 8 * S, parity);
+    if (!ok) mbar_wait_slow(B.sbase + OFF_FULL + 8 * S, parity);
     const uint32_t sp = B.stage + S * B.row_bytes + 48 * tid;
     uint4 q0, q1, q2;
     uint32_t wl, wr;
@@ -202,16 +334,27 @@ __device__ __forceinline__ uint32_t load_row(const Band &B, int q, int grp, uint
     asm volatile("ld.shared.u32 %0, [%1+-4];" : "=r"(wl) : "r"(sp));
     asm volatile("ld.shared.u32 %0, [%1+48];" : "=r"(wr) : "r"(sp));
     uint32_t a[16];
-    gray4(q0.x, q0.y, q0.z, a[0], a[1], a[2], a[3]);
-    gray4(q0.w, q1.x, q1.y, a[4], a[5], a[6], a[7]);
-    gray4(q1.z, q1.w, q2.x, a[8], a[9], a[10], a[11]);
-    gray4(q2.y, q2.z, q2.w, a[12], a[13], a[14], a[15]);
+    const GrayK &K = B.K;
+#if K1_STUB
+    // timing experiment only: the streaming skeleton without the arithmetic
+    R.E[0] = q0.x ^ q1.x ^ q2.x; R.E[1] = q0.y ^ q1.y ^ q2.y; R.E[2] = q0.z ^ q1.z ^ q2.z; R.E[3] = q0.w ^ q1.w ^ q2.w;
+    R.O[0] = R.O[1] = R.O[2] = R.O[3] = wl; R.LR = wr;
+    __syncwarp();
+    const uint32_t ticket0 = stage_arrive(B.sbase + OFF_CNT + 8 * S, (tid & 31) == 0 ? 1u : 0u, wl ^ wr);
+    ok = mbar_try(nbar, npar);
+    return ticket0;
+#endif
+    gray4(K, q0.x, q0.y, q0.z, a[0], a[1], a[2], a[3]);
+    gray4(K, q0.w, q1.x, q1.y, a[4], a[5], a[6], a[7]);
+    gray4(K, q1.z, q1.w, q2.x, a[8], a[9], a[10], a[11]);
+    gray4(K, q2.y, q2.z, q2.w, a[12], a[13], a[14], a[15]);
     // neighbour pixels x-1 and x+16 (REFLECT_101 at the frame edges: x=-1 -> 1, x=W -> W-2)
-    uint32_t aL = __dp2a_hi(C_GR, wl, __dp2a_lo(C_0B, wl, RND));
-    uint32_t aR = __dp2a_hi(C_R0, wr, __dp2a_lo(C_BG, wr, RND));
+    uint32_t aL = __dp2a_hi(K.gr, wl, __dp2a_lo(K.ob, wl, K.rnd));
+    uint32_t aR = __dp2a_hi(K.r0, wr, __dp2a_lo(K.bg, wr, K.rnd));
     // every lane of this warp has its bytes in registers: count the warp off the stage (result used much later)
     __syncwarp();
     const uint32_t ticket = stage_arrive(B.sbase + OFF_CNT + 8 * S, (tid & 31) == 0 ? 1u : 0u, aL ^ aR);
+    ok = mbar_try(nbar, npar);               // next row's stage: checked at the top of the next step
     aL = first ? a[1] : aL;
     aR = last ? a[14] : aR;
 #pragma unroll
@@ -220,10 +363,14 @@ __device__ __forceinline__ uint32_t load_row(const Band &B, int q, int grp, uint
         R.O[g] = __byte_perm(a[4 * g + 1], a[4 * g + 3], 0x7632);
     }
     R.LR = __byte_perm(aL, aR, 0x7632);
-    // thumbnail tap row?  info: bit0 tap, bit1 second row of its pair, bits 2-13 vertical weight, bits 16-24 thumbnail row
-    uint32_t info;
-    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(info) : "r"(B.sbase + OFF_INFO + 4 * q));
-    if (info & 1u) {
+    // general form of the thumbnail (any tap weights): handled when the row is loaded
+    // info: bit0 tap, bit1 second row of its pair, bits 2-13 vertical weight, bits 16-24 thumbnail row
+    uint32_t info = 0;
+    if (!PAIR) asm volatile("ld.shared.u32 %0, [%1];" : "=r"(info) : "r"(B.sbase + OFF_INFO + 4 * q));
+#if K1_NOTHUMB
+    info = 0;                                 // timing experiment only
+#endif
+    if (!PAIR && (info & 1u)) {
         uint4 gw;
         gw.x = __byte_perm(R.E[0], R.O[0], 0x6240); gw.y = __byte_perm(R.E[1], R.O[1], 0x6240);
         gw.z = __byte_perm(R.E[2], R.O[2], 0x6240); gw.w = __byte_perm(R.E[3], R.O[3], 0x6240);
@@ -256,7 +403,11 @@ __device__ __forceinline__ uint32_t load_row(const Band &B, int q, int grp, uint
 template <int POS>
 __device__ __forceinline__ void release_finish(const Band &B, int q, int grp, uint32_t ticket)
 {
+#if K1_BANDPAR
+    if (ticket == 1u && q + NRS < B.nseq) issue_row(B.sbase, q + NRS, 3 * grp + POS);
+#else
     if (ticket == 1u && q + NRS < B.nseq) issue_row(B, q + NRS, 3 * grp + POS);
+#endif
 }
 
 __device__ __forceinline__ uint8_t sat_rne(float v)
@@ -274,32 +425,7 @@ __device__ __forceinline__ uint32_t masked_sum(const uint32_t *P, const uint32_t
     return s;
 }
 
-// INTER_AREA cell (dy,dx) of frame `src` in the library's exact float32 order, one warp per cell
-__device__ float area_cell_exact(const uint8_t *src, size_t pitch, const ShapeTables *tab, int dy, int dx, int lane)
-{
-    const AreaCell cy = tab->ay[dy], cx = tab->ax[dx];
-    const int r0 = cy.has_head ? cy.s1 - 1 : cy.s1, r1 = cy.has_tail ? cy.s2 : cy.s2 - 1;
-    float sum = 0.f;
-    for (int rb = r0; rb <= r1; rb += 32) {
-        const int r = rb + lane;
-        float term = 0.f;
-        if (r <= r1) {
-            const uint8_t *p = src + (size_t)r * pitch;
-            auto gray = [&](int x) { const uint8_t *q = p + 3 * x; return (float)((3735u * q[0] + 19235u * q[1] + 9798u * q[2] + 16384u) >> 15); };
-            float buf = 0.f;
-            if (cx.has_head) buf = __fadd_rn(buf, __fmul_rn(gray(cx.s1 - 1), cx.ah));
-            for (int x = cx.s1; x < cx.s2; x++) buf = __fadd_rn(buf, __fmul_rn(gray(x), cx.am));
-            if (cx.has_tail) buf = __fadd_rn(buf, __fmul_rn(gray(cx.s2), cx.at));
-            const float beta = (cy.has_head && r == r0) ? cy.ah : ((cy.has_tail && r == cy.s2) ? cy.at : cy.am);
-            term = __fmul_rn(beta, buf);
-        }
-        const int cnt = min(32, r1 - rb + 1);
-        for (int i = 0; i < cnt; i++) sum = __fadd_rn(sum, __shfl_sync(0xffffffffu, term, i));
-    }
-    return sum;
-}
-
-template <int MAXT, int MINB, int JT>
+template <int MAXT, int MINB, int JT, bool PAIR>
 __global__ void __launch_bounds__(MAXT, MINB) k1_fused_kernel(K1Params P)
 {
     extern __shared__ __align__(128) uint8_t smem[];
@@ -310,38 +436,53 @@ __global__ void __launch_bounds__(MAXT, MINB) k1_fused_kernel(K1Params P)
     const int H = P.H, W = P.W;
     const int own0 = tab->row_owner_begin[b], own1 = tab->row_owner_begin[b + 1];
     const int n = own1 - own0, nseq = n + 2;
-    const int ty_begin = tab->thumb_row_begin[b], nty = tab->thumb_row_begin[b + 1] - ty_begin;
-    const uint32_t sbase = smem_u32(smem);
+    uint32_t sbase;                         // opaque, or the compiler recomputes the shared window address at every use
+#if K1_OPAQUE_BASE
+    asm volatile("mov.u32 %0, %1;" : "=r"(sbase) : "r"(smem_u32(smem)));
+#else
+    sbase = smem_u32(smem);
+#endif
     const uint8_t *frame = P.bgr + (size_t)f * P.fstride;
 
     Band B;
     B.sbase = sbase; B.stage = sbase + HDR; B.slot = sbase + HDR + NRS * P.row_bytes + 64 + SLOT * tid;
-    B.row_bytes = P.row_bytes; B.W = W; B.H = H; B.own0 = own0;
-    B.nseq = nseq; B.nw = nw; B.frame = frame; B.pitch = P.pitch;
+    B.row_bytes = P.row_bytes; B.nseq = nseq;
+    B.K.load();
+    B.todd = tab->lx[0].i0 & 1;
+#if !K1_BANDPAR
+    B.H = H; B.own0 = own0; B.frame = frame; B.pitch = P.pitch;
     asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(B.pol_stream));
     asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(B.pol_keep));
+#endif
 
     if (tid == 0) {
         for (int s = 0; s < NRS; s++) {
             mbar_init(sbase + OFF_FULL + 8 * s, 1);
             mbar_init(sbase + OFF_CNT + 8 * s, nw);
         }
+        BandPar *bp = (BandPar *)(smem + OFF_PAR);
+        unsigned long long pol_stream, pol_keep;
+        asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol_stream));
+        asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(pol_keep));
+        bp->frame = frame; bp->pitch = P.pitch; bp->pol_stream = pol_stream; bp->pol_keep = pol_keep; bp->tab = tab;
+        bp->row_bytes = P.row_bytes; bp->own0 = own0; bp->H = H; bp->nseq = nseq;
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+#if K1_BANDPAR
+#pragma unroll 1
+        for (int q = 0; q < NRS; q++) issue_row(sbase, q, q);
+#else
         for (int q = 0; q < NRS; q++) issue_row(B, q, q);
+#endif
     }
     if (tid < 32) ((int *)(smem + OFF_CELL))[tid] = 0;
-    // tap rows of this band's thumbnail rows (top tap row owned by the band, bottom tap = the row below it)
-    {
-        uint32_t *info = (uint32_t *)(smem + OFF_INFO);
-        for (int q = tid; q < nseq; q += nthr) info[q] = 0;
-        __syncthreads();
-        for (int j = tid; j < nty; j += nthr) {
-            const LinTap vy = tab->ly[ty_begin + j];
-            const int q0 = vy.i0 - (own0 - 1);
-            info[q0] = 1u | ((uint32_t)vy.a0 << 2) | ((uint32_t)(ty_begin + j) << 16);
-            info[q0 + 1] = 3u | ((uint32_t)vy.a1 << 2) | ((uint32_t)(ty_begin + j) << 16);
-        }
+    if (tid == 32) ((uint32_t *)(smem + OFF_MISC))[1] = 0;          // warps that finished the band
+    // thumbnail role of the band's rows: the top tap row must be owned by this band, the bottom tap is the row below it
+    for (int q = tid; q < nseq; q += nthr) {
+        const int r = own0 - 1 + q;
+        uint32_t v = (r >= 0 && r < H) ? tab->rowinfo[r] : 0u;
+        if (q == 0 || (q == 1 && (v & 2u)) || (q == nseq - 1 && !(v & 2u))) v = 0;
+        ((uint32_t *)(smem + OFF_INFO))[q] = v;
     }
     // this thread's thumbnail columns
     Thumb<JT> T;
@@ -353,7 +494,8 @@ __global__ void __launch_bounds__(MAXT, MINB) k1_fused_kernel(K1Params P)
         for (int k = 0; k < JT; k++) {
             const LinTap t = tab->lx[min(tx0 + k, AVD_T - 1)];
             const bool ok = k < T.ntx;
-            T.addr[k] = B.slot + (ok ? (uint32_t)(t.i0 - 16 * tid) : 0u);
+            const int rel = t.i0 - 16 * tid;                            // left tap, relative to the strip
+            T.addr[k] = B.slot + (ok ? (uint32_t)(PAIR ? 2 * (rel >> 1) : rel) : 0u);   // pair form: 16-bit lane rel/2 (even) or (rel-1)/2 (odd)
             T.a0[k] = (uint32_t)t.a0; T.a1[k] = (uint32_t)t.a1; T.u0[k] = 0;
         }
     }
@@ -375,9 +517,13 @@ __global__ void __launch_bounds__(MAXT, MINB) k1_fused_kernel(K1Params P)
     const int wh = 32 * own0 - b * H;                     // weight of the head row (sequence row 0), 1/32 units
     const int wt = (b + 1) * H - 32 * (own1 - 1);         // weight of the last owned row, 1/32 units (32 = full)
 
-    uint32_t t0 = load_row<0>(B, 0, 0, 0u, tid, first, last, R0, T);
+    auto full_bar = [&](int st) { return sbase + OFF_FULL + 8 * st; };
+    uint32_t par = 0;
+    int grp = 0;
+    uint32_t ok = mbar_try(full_bar(0), 0u);
+    uint32_t t0 = load_row<0, JT, PAIR>(B, 0, 0, 0u, ok, full_bar(1), 0u, tid, first, last, R0, T);
     release_finish<0>(B, 0, 0, t0);
-    uint32_t t1 = load_row<1>(B, 1, 0, 0u, tid, first, last, R1, T);
+    uint32_t t1 = load_row<1, JT, PAIR>(B, 1, 0, 0u, ok, full_bar(2), 0u, tid, first, last, R1, T);
     release_finish<1>(B, 1, 0, t1);
     int tv = (int)row_sum(R0) - (int)row_sum(R1);         // vertical part of sum L telescopes to 4 rows per band
     int mcA = 0, mcB = 0;                                  // cell sums in 1/32 units
@@ -389,7 +535,26 @@ __global__ void __launch_bounds__(MAXT, MINB) k1_fused_kernel(K1Params P)
         mcA = wh * (int)sa; mcB = wh * (int)(st - sa);
     }
     // at the last sequence row: C is the last owned row, D the bottom halo
+    // thumbnail role of sequence row q (pair-sum form: looked up when the row is the centre row)
+    auto row_info = [&](int qq) {
+        uint32_t v = 0;
+        if (PAIR) asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(sbase + OFF_INFO + 4 * qq));
+        return v;
+    };
     auto band_end = [&](const RowSet &C, const RowSet &D) {
+#if !K1_NOTHUMB && !K1_STUB
+        const uint32_t infoD = row_info(nseq - 1);       // the bottom halo row is never a centre row
+        if (PAIR && (infoD & 1u)) {
+            uint32_t X[4];
+#pragma unroll
+            for (int g = 0; g < 4; g++) {
+                const uint32_t orr = g == 3 ? __byte_perm(D.E[3], D.LR, 0x7632) : __byte_perm(D.E[g], D.E[g + 1], 0x5432);
+                X[g] = B.todd ? D.O[g] + orr : D.E[g] + D.O[g];
+            }
+            thumb_pairs_store<JT>(B, X);
+            thumb_pairs_finish<JT>(T, infoD);
+        }
+#endif
         tv += (int)row_sum(D) - (int)row_sum(C);
         uint32_t Pp[4];
 #pragma unroll
@@ -398,81 +563,74 @@ __global__ void __launch_bounds__(MAXT, MINB) k1_fused_kernel(K1Params P)
         mcA -= (32 - wt) * (int)sa; mcB -= (32 - wt) * (int)(st - sa);
     };
 
-    uint32_t par = 0;
-    int q = 2, grp = 0;
+    int q = 2;
     while (true) {
-        uint32_t tk = load_row<2>(B, q, grp, par, tid, first, last, R2, T);
-        lap_step(R0, R1, R2, A);
+        const int ng = grp + 1 == NGRP ? 0 : grp + 1;
+        const uint32_t np = grp + 1 == NGRP ? par ^ 1u : par;
+        uint32_t tk = load_row<2, JT, PAIR>(B, q, grp, par, ok, full_bar(3 * ng), np, tid, first, last, R2, T);
+        lap_step<JT, PAIR>(B, R0, R1, R2, A, T, row_info(q - 1));
         release_finish<2>(B, q, grp, tk);
         if (q == nseq - 1) { band_end(R1, R2); break; }
-        q++;
-        if (++grp == NGRP) { grp = 0; par ^= 1u; }
-        tk = load_row<0>(B, q, grp, par, tid, first, last, R0, T);
-        lap_step(R1, R2, R0, A);
+        q++; grp = ng; par = np;
+        tk = load_row<0, JT, PAIR>(B, q, grp, par, ok, full_bar(3 * grp + 1), par, tid, first, last, R0, T);
+        lap_step<JT, PAIR>(B, R1, R2, R0, A, T, row_info(q - 1));
         release_finish<0>(B, q, grp, tk);
         if (q == nseq - 1) { band_end(R2, R0); break; }
         q++;
-        tk = load_row<1>(B, q, grp, par, tid, first, last, R1, T);
-        lap_step(R2, R0, R1, A);
+        tk = load_row<1, JT, PAIR>(B, q, grp, par, ok, full_bar(3 * grp + 2), par, tid, first, last, R1, T);
+        lap_step<JT, PAIR>(B, R2, R0, R1, A, T, row_info(q - 1));
         release_finish<1>(B, q, grp, tk);
         if (q == nseq - 1) { band_end(R0, R1); break; }
         q++;
     }
 
-    // ---- per-thread totals ----
+    // ---- per-thread totals; no block barrier: every warp publishes its own sums, the last one finishes the cells ----
     {
         const uint32_t sa = masked_sum(A.cs, mA), st = masked_sum(A.cs, mAll);
         mcA += 32 * (int)sa; mcB += 32 * (int)(st - sa);
     }
     long long sumL = (long long)tv + (long long)lanes_sum(A.aLR) - (long long)(A.aE0 & 0xffffu) - (long long)(A.aO3 >> 16);
-    unsigned long long sq = (unsigned long long)A.ll + 512ull * A.hl + 65536ull * A.hh;
-    if (!active) { sumL = 0; sq = 0; mcA = 0; mcB = 0; }
+    // sum (L+1020)^2 -> sum L^2 over this thread's n x 16 pixels
+    long long sumL2 = (long long)((unsigned long long)A.ll + 512ull * A.hl + 65536ull * A.hh) - 2040ll * sumL - 1040400ll * (16ll * n);
     int *cellM = (int *)(smem + OFF_CELL);
     if (active) {
         atomicAdd(&cellM[cA], mcA);
         if (kA < 8) atomicAdd(&cellM[cA + 1], mcB);
+    } else {
+        sumL = 0; sumL2 = 0;
     }
-    for (int o = 16; o; o >>= 1) { sumL += __shfl_down_sync(0xffffffffu, sumL, o); sq += __shfl_down_sync(0xffffffffu, sq, o); }
-    unsigned long long *red = (unsigned long long *)(smem + OFF_RED);
-    if (lane == 0) { red[tid >> 5] = (unsigned long long)sumL; red[8 + (tid >> 5)] = sq; }
-    __syncthreads();
-    uint32_t *misc = (uint32_t *)(smem + OFF_MISC);
-    if (tid < 32) {
-        long long s1 = tid < nw ? (long long)red[tid] : 0;
-        unsigned long long s2 = tid < nw ? red[8 + tid] : 0;
-        for (int o = 16; o; o >>= 1) { s1 += __shfl_down_sync(0xffffffffu, s1, o); s2 += __shfl_down_sync(0xffffffffu, s2, o); }
-        if (tid == 0) {
-            const long long npx = (long long)n * W;
-            const long long sumL2 = (long long)s2 - 2040ll * s1 - 1040400ll * npx;       // s2 = sum (L+1020)^2
-            atomicAdd((unsigned long long *)&P.rec[f].lap_sum, (unsigned long long)s1);
-            atomicAdd((unsigned long long *)&P.rec[f].lap_sumsq, (unsigned long long)sumL2);
-        }
-        // ---- INTER_AREA destination row b, column tid ----
-        const int M = cellM[tid];
-        uint8_t out;
-        bool close = false;
-        if (tab->area_int) {
-            out = sat_rne(__fmul_rn((float)(M >> 5), tab->inv_area));
-        } else {
-            const double v = (double)M / ((double)H * (double)sx);
-            const double fl = floor(v);
-            const double bound = v * (2.0 * (double)(sx + n + 5) * 5.9604644775390625e-08) + 1e-9;
-            close = fabs(v - fl - 0.5) <= bound;
-            out = (uint8_t)min(255, (int)floor(v + 0.5));
-        }
-        P.area32[(size_t)f * 1024 + b * 32 + tid] = out;
-        const uint32_t mask = __ballot_sync(0xffffffffu, close);
-        if (tid == 0) misc[0] = mask;
+    for (int o = 16; o; o >>= 1) { sumL += __shfl_down_sync(0xffffffffu, sumL, o); sumL2 += __shfl_down_sync(0xffffffffu, sumL2, o); }
+    uint32_t is_last = 0;
+    if (lane == 0) {
+        atomicAdd((unsigned long long *)&P.rec[f].lap_sum, (unsigned long long)sumL);
+        atomicAdd((unsigned long long *)&P.rec[f].lap_sumsq, (unsigned long long)sumL2);
     }
-    __syncthreads();
-    uint32_t mask = misc[0];
-    while (mask) {                                      // rare: cells too close to a rounding boundary
-        const int dx = __ffs(mask) - 1;
-        mask &= mask - 1;
-        if ((dx % nw) != (tid >> 5)) continue;
-        const float v = area_cell_exact(frame, P.pitch, tab, b, dx, lane);
-        if (lane == 0) P.area32[(size_t)f * 1024 + b * 32 + dx] = sat_rne(v);
+    __syncwarp();
+    if (lane == 0) {
+        uint32_t old;
+        asm volatile("atom.acq_rel.cta.shared::cta.add.u32 %0, [%1], 1;" : "=r"(old) : "r"(sbase + OFF_MISC + 4) : "memory");
+        is_last = old == (uint32_t)(nw - 1);
     }
+    is_last = __shfl_sync(0xffffffffu, is_last, 0);
+    if (!is_last) return;
+
+    // ---- INTER_AREA destination row b, column `lane` (this warp is the last one of the band) ----
+    const int M = cellM[lane];
+    uint32_t out;
+    bool close = false;
+    if (tab->area_int) {
+        out = sat_rne(__fmul_rn((float)(M >> 5), tab->inv_area));
+    } else {
+        // exact mean v = M / (H*sx).  close <=> |frac(v) - 0.5| <= 17/16 (sx+n+5) 2^-24 v, all in integers (times 2 H sx)
+        const uint32_t Dn = (uint32_t)H * (uint32_t)sx;
+        const uint32_t k = (uint32_t)M / Dn, r = (uint32_t)M - k * Dn;
+        const int d2 = (int)(2u * r) - (int)Dn;
+        const uint32_t bound = (uint32_t)(((unsigned long long)(uint32_t)M * (uint32_t)(17 * (sx + n + 5))) >> 27) + 2u;
+        close = (uint32_t)abs(d2) <= bound;
+        out = k + (d2 >= 0 ? 1u : 0u);
+    }
+    P.area32[(size_t)f * 1024 + b * 32 + lane] = (uint8_t)out;
+    P.areaflag[(size_t)f * 1024 + b * 32 + lane] = close ? 1 : 0;   // recomputed in the library's float32 order by k1_hash_finalize
 }
 
 }  // namespace
@@ -496,12 +654,12 @@ bool k1_fused_supported(int H, int W, size_t pitch, size_t fstride, const void *
     return true;
 }
 
-template <int MAXT, int MINB, int JT>
+template <int MAXT, int MINB, int JT, bool PAIR>
 static int k1_launch(avd_ctx *ctx, const K1Params &P, int n, size_t smem, int threads, cudaStream_t st)
 {
     static size_t smem_set = 0;
     if (smem > smem_set) {
-        AVD_CUDA(ctx, cudaFuncSetAttribute(k1_fused_kernel<MAXT, MINB, JT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        AVD_CUDA(ctx, cudaFuncSetAttribute(k1_fused_kernel<MAXT, MINB, JT, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         smem_set = smem;
     }
     for (int f0 = 0; f0 < n; f0 += 65535) {                          // grid.y limit
@@ -509,25 +667,38 @@ static int k1_launch(avd_ctx *ctx, const K1Params &P, int n, size_t smem, int th
         K1Params Q = P;
         Q.bgr = P.bgr + (size_t)f0 * P.fstride; Q.rec = P.rec + f0;
         Q.thumbs = P.thumbs + (size_t)f0 * AVD_T * AVD_T; Q.area32 = P.area32 + (size_t)f0 * 1024;
-        AVD_LAUNCH(ctx, "k1_fused", st, (k1_fused_kernel<MAXT, MINB, JT><<<dim3(AVD_D, nb), threads, smem, st>>>(Q)));
+        Q.areaflag = P.areaflag + (size_t)f0 * 1024;
+        AVD_LAUNCH(ctx, "k1_fused", st, (k1_fused_kernel<MAXT, MINB, JT, PAIR><<<dim3(AVD_D, nb), threads, smem, st>>>(Q)));
     }
     return AVD_OK;
 }
 
 int k1_fused(avd_ctx *ctx, const uint8_t *d_bgr, int n, int H, int W, size_t pitch, size_t fstride,
              const ShapeTables *tab, const ShapeTables *htab, avd_sample_rec *d_rec, uint8_t *d_thumbs,
-             uint8_t *d_area32, cudaStream_t st)
+             uint8_t *d_area32, uint8_t *d_areaflag, cudaStream_t st)
 {
     K1Params P{};
     P.bgr = d_bgr; P.pitch = pitch; P.fstride = fstride; P.H = H; P.W = W; P.row_bytes = 3 * W;
-    P.tab = tab; P.rec = d_rec; P.thumbs = d_thumbs; P.area32 = d_area32;
+    P.tab = tab; P.rec = d_rec; P.thumbs = d_thumbs; P.area32 = d_area32; P.areaflag = d_areaflag;
     const size_t smem = k1_smem_bytes(W);
     const int threads = (W / 16 + 31) / 32 * 32;
     const int jt = htab->strip_ntx_max;
+    // pair-sum thumbnail: every horizontal tap pair is (1024, 1024) and all left taps have the same parity
+    bool pair = true;
+    for (int i = 0; i < AVD_T; i++)
+        if (htab->lx[i].a0 != 1024 || htab->lx[i].a1 != 1024 || ((htab->lx[i].i0 ^ htab->lx[0].i0) & 1)) pair = false;
     if (threads <= 128) {                                            // <= 2048 px wide
-        if (jt <= 3) return k1_launch<128, K1_MINB, 3>(ctx, P, n, smem, threads, st);
-        return k1_launch<128, K1_MINB, 4>(ctx, P, n, smem, threads, st);
+        if (pair) {
+            if (jt <= 3) return k1_launch<128, K1_MINB, 3, true>(ctx, P, n, smem, threads, st);
+            return k1_launch<128, K1_MINB, 4, true>(ctx, P, n, smem, threads, st);
+        }
+        if (jt <= 3) return k1_launch<128, K1_MINB, 3, false>(ctx, P, n, smem, threads, st);
+        return k1_launch<128, K1_MINB, 4, false>(ctx, P, n, smem, threads, st);
     }
-    if (jt <= 2) return k1_launch<256, 2, 2>(ctx, P, n, smem, threads, st);
-    return k1_launch<256, 2, 3>(ctx, P, n, smem, threads, st);
+    if (pair) {
+        if (jt <= 2) return k1_launch<256, 2, 2, true>(ctx, P, n, smem, threads, st);
+        return k1_launch<256, 2, 3, true>(ctx, P, n, smem, threads, st);
+    }
+    if (jt <= 2) return k1_launch<256, 2, 2, false>(ctx, P, n, smem, threads, st);
+    return k1_launch<256, 2, 3, false>(ctx, P, n, smem, threads, st);
 }

@@ -21,6 +21,8 @@ template <int OP> __device__ __forceinline__ uint32_t op1(uint32_t a, uint32_t b
     else if (OP == 7) { float f; asm volatile("fma.rn.f32 %0, %1, %2, %3;" : "=f"(f) : "f"(__uint_as_float(a)), "f"(__uint_as_float(b)), "f"(__uint_as_float(c))); d = __float_as_uint(f); }
     else if (OP == 8) { float f; asm volatile("add.rn.f32 %0, %1, %2;" : "=f"(f) : "f"(__uint_as_float(a)), "f"(__uint_as_float(c))); d = __float_as_uint(f); }
     else if (OP == 9) asm volatile("vadd2.u32.u32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));   // SIMD video add (emulated?)
+    else if (OP == 12) asm volatile("mad.lo.u32 %0, %1, 1, %2;" : "=r"(d) : "r"(a), "r"(c));          // IMAD.IADD ?
+    else if (OP == 13) asm volatile("mad.lo.u32 %0, %1, -4, %2;" : "=r"(d) : "r"(c), "r"(a));         // IMAD imm
     else if (OP == 10) asm volatile("{.reg .b32 t; add.u16x2 %0, %1, %2;}" : "=r"(d) : "r"(a), "r"(c));
     else d = a;
     return d;
@@ -102,6 +104,12 @@ int main()
     run<0, 2, 2, 1>("2dp2a+prmt", out, cyc);
     run<0, 2, 1, 2>("dp2a+2prmt", out, cyc);
     run<4, 2, 1, 2>("imad+2prmt", out, cyc);
+    run<12, 11, 1, 0>("imad.iadd", out, cyc);
+    run<13, 11, 1, 0>("imad-4", out, cyc);
+    run<0, 12, 1, 1>("dp2a+imad.iadd", out, cyc);
+    run<0, 13, 1, 1>("dp2a+imad-4", out, cyc);
+    run<2, 12, 1, 1>("prmt+imad.iadd", out, cyc);
+    run<8, 12, 1, 1>("fadd+imad.iadd", out, cyc);
     run<0, 2, 1, 1>("dp2a+prmt", out, cyc, 256);
     run<0, 2, 1, 1>("dp2a+prmt", out, cyc, 128);
     run<0, 2, 1, 1>("dp2a+prmt", out, cyc, 64);
