@@ -193,7 +193,7 @@ void avd_destroy(avd_ctx *ctx)
     cudaDeviceSynchronize();
     for (auto &kv : ctx->tables) cudaFree(kv.second);
     cudaFree(ctx->gray); cudaFree(ctx->area_rows); cudaFree(ctx->k2_ws); cudaFree(ctx->ring);
-    cudaFree(ctx->thumbs); cudaFree(ctx->recs); cudaFree(ctx->area32); cudaFree(ctx->areaflag);
+    cudaFree(ctx->thumbs); cudaFree(ctx->recs); cudaFree(ctx->area32); cudaFree(ctx->fixlist);
     for (int i = 0; i < 4; i++) { cudaEventDestroy(ctx->ev_copied[i]); cudaEventDestroy(ctx->ev_free[i]); }
     cudaStreamDestroy(ctx->compute); cudaStreamDestroy(ctx->copy);
     cudaGetLastError();
@@ -292,19 +292,21 @@ int avd_frames_features(avd_ctx *ctx, const uint8_t *d_bgr, int n, int H, int W,
         if ((rc = avd_ensure(ctx, (void **)&ctx->area32, &ctx->area32_cap, (size_t)n * 1024))) return rc;
         d_area32 = ctx->area32;
     }
-    if ((rc = k1_rec_init(ctx, d_rec, n, st))) return rc;
     K1FixArgs fix{d_bgr, row_pitch, frame_stride, tab, nullptr};
-    if (ctx->k1_mode == 0 && k1_fused_supported(H, W, row_pitch, frame_stride, d_bgr, htab)) {
-        if ((rc = avd_ensure(ctx, (void **)&ctx->areaflag, &ctx->areaflag_cap, (size_t)n * 1024))) return rc;
-        fix.flags = ctx->areaflag;
-        rc = k1_fused(ctx, d_bgr, n, H, W, row_pitch, frame_stride, tab, htab, d_rec, d_thumbs, d_area32, ctx->areaflag, st);
+    const bool streaming = ctx->k1_mode == 0 && k1_fused_supported(H, W, row_pitch, frame_stride, d_bgr, htab);
+    if (streaming) {
+        if ((rc = avd_ensure(ctx, (void **)&ctx->fixlist, &ctx->fixlist_cap, ((size_t)n * 1024 + 1) * sizeof(uint32_t)))) return rc;
+        fix.list = ctx->fixlist;
     }
+    if ((rc = k1_rec_init(ctx, d_rec, n, streaming ? ctx->fixlist : nullptr, st))) return rc;
+    if (streaming)
+        rc = k1_fused(ctx, d_bgr, n, H, W, row_pitch, frame_stride, tab, htab, d_rec, d_thumbs, d_area32, ctx->fixlist, st);
     else if ((ctx->k1_mode == 0 || ctx->k1_mode == 2) && k1_banded_supported(H, W, row_pitch, frame_stride, d_bgr))
         rc = k1_banded(ctx, d_bgr, n, H, W, row_pitch, frame_stride, tab, htab, d_rec, d_thumbs, d_area32, st);
     else
         rc = k1_generic(ctx, d_bgr, n, H, W, row_pitch, frame_stride, tab, htab, d_rec, d_thumbs, d_area32, st);
     if (rc) return rc;
-    return k1_hash_finalize(ctx, d_area32, n, d_prev_hash, d_rec, fix.flags ? &fix : nullptr, st);
+    return k1_hash_finalize(ctx, d_area32, n, d_prev_hash, d_rec, fix.list ? &fix : nullptr, st);
 }
 
 int avd_flow_stats(avd_ctx *ctx, const uint8_t *d_thumbs, int n, const uint8_t *d_prev_thumb,

@@ -65,7 +65,7 @@ struct avd_ctx {
     uint8_t *thumbs = nullptr; size_t thumbs_cap = 0;
     avd_sample_rec *recs = nullptr; size_t recs_cap = 0;
     uint8_t *area32 = nullptr; size_t area32_cap = 0;
-    uint8_t *areaflag = nullptr; size_t areaflag_cap = 0;
+    uint32_t *fixlist = nullptr; size_t fixlist_cap = 0;   // streaming K1: [0] = count, then uncertified cells
     // optional per-kernel timing (avd_profile_enable): CUDA events around every launch, on its stream
     bool profiling = false;
     struct ProfRec { const char *name; cudaEvent_t a, b; };
@@ -109,13 +109,13 @@ int avd_ensure(avd_ctx *ctx, void **p, size_t *cap, size_t need);   // grow-only
 int avd_get_tables(avd_ctx *ctx, int H, int W, const ShapeTables **dev, const ShapeTables **host);
 
 // k1_generic.cu
-int k1_rec_init(avd_ctx *ctx, avd_sample_rec *d_rec, int n, cudaStream_t st);
+int k1_rec_init(avd_ctx *ctx, avd_sample_rec *d_rec, int n, uint32_t *d_fixcount, cudaStream_t st);
 int k1_generic(avd_ctx *ctx, const uint8_t *d_bgr, int n, int H, int W, size_t pitch, size_t fstride,
                const ShapeTables *tab, const ShapeTables *htab, avd_sample_rec *d_rec, uint8_t *d_thumbs,
                uint8_t *d_area32, cudaStream_t st);
 int k1_gray_only(avd_ctx *ctx, const uint8_t *d_bgr, int H, int W, size_t pitch, uint8_t *d_gray, cudaStream_t st);
-// d_areaflag != NULL: cells flagged by the streaming kernel are first recomputed from the frames (exact float32 order)
-struct K1FixArgs { const uint8_t *bgr; size_t pitch, fstride; const ShapeTables *tab; const uint8_t *flags; };
+// fix != NULL: the cells listed by the streaming kernel are first recomputed from the frames (exact float32 order)
+struct K1FixArgs { const uint8_t *bgr; size_t pitch, fstride; const ShapeTables *tab; const uint32_t *list; };
 int k1_hash_finalize(avd_ctx *ctx, uint8_t *d_area32, int n, const uint32_t *d_prev_hash,
                      avd_sample_rec *d_rec, const K1FixArgs *fix, cudaStream_t st);
 // k1_fused.cu (streaming kernel: W % 64 == 0, 640 <= W <= 4096, 640 <= H <= 4096) and k1_banded.cu (W % 16 == 0)
@@ -126,7 +126,7 @@ int k1_banded(avd_ctx *ctx, const uint8_t *d_bgr, int n, int H, int W, size_t pi
               uint8_t *d_area32, cudaStream_t st);
 int k1_fused(avd_ctx *ctx, const uint8_t *d_bgr, int n, int H, int W, size_t pitch, size_t fstride,
              const ShapeTables *tab, const ShapeTables *htab, avd_sample_rec *d_rec, uint8_t *d_thumbs,
-             uint8_t *d_area32, uint8_t *d_areaflag, cudaStream_t st);
+             uint8_t *d_area32, uint32_t *d_fixlist, cudaStream_t st);
 // k2_flow.cu
 int k2_flow(avd_ctx *ctx, const uint8_t *d_prev, const uint8_t *d_next, size_t prev_stride, size_t next_stride,
             int n_pairs, bool shared_chain, avd_sample_rec *d_rec_first, float *d_flow_out, cudaStream_t st);

@@ -28,8 +28,8 @@
 // sums; float32 evaluation in the library's order differs from it by at most (nx+ny+4) * 2^-24 relative
 // (standard forward error bound of recursive summation, nx/ny = taps per cell), so whenever the exact mean is
 // farther than that bound (taken with a 17/16 margin) from a rounding boundary k+0.5 the library's byte is
-// round(mean).  The few cells (~0.2 %) that are closer are flagged and recomputed in the library's exact float32
-// order by the hash kernel that follows (k1_generic.cu), off this kernel's critical path.
+// round(mean).  The few cells (~0.2 %) that are closer are listed and recomputed in the library's exact float32
+// order by area_fix_kernel (k1_generic.cu), off this kernel's critical path.
 #include "avd_internal.h"
 
 namespace {
@@ -77,7 +77,9 @@ struct K1Params {
     int H, W, row_bytes;
     const ShapeTables *tab;
     avd_sample_rec *rec;
-    uint8_t *thumbs, *area32, *areaflag;
+    uint8_t *thumbs, *area32;
+    uint32_t *fixlist;                // [0] = count (zeroed by k1_rec_init), then frame * 1024 + cell
+    int frame0;
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -201,33 +203,39 @@ template <int JT> struct Thumb {
 
 // ---- thumbnail, pair-sum form (W a multiple of 640: every horizontal tap pair has weights 1024/1024, so the
 // horizontal pass is 1024 * (p[x0] + p[x0+1]) and those pair sums already exist in 16-bit lanes: E+O holds the pairs
-// starting at even offsets, O+orr the pairs starting at odd offsets).  The four registers go to the thread's private
-// slot and each thumbnail column of the thread reads its lane back at its own (per-thread constant) offset.
-template <int JT>
-__device__ __forceinline__ void thumb_pairs_store(const Band &B, const uint32_t *X)
+// starting at even offsets, O+orr the pairs starting at odd offsets).  A thumbnail row is produced when its bottom tap
+// row is the centre row C: its top tap row is then still in registers as U.  Both rows' pair sums go to the thread's
+// private slot and each thumbnail column of the thread reads its lanes back at its own (per-thread constant) offset;
+// the loads are issued before the Laplacian arithmetic and consumed after it.
+__device__ __forceinline__ void pair_sums(const RowSet &R, const uint32_t *orr, int todd, uint32_t *X)
 {
-    asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(B.slot), "r"(X[0]), "r"(X[1]), "r"(X[2]), "r"(X[3]) : "memory");
+#pragma unroll
+    for (int g = 0; g < 4; g++) X[g] = todd ? R.O[g] + orr[g] : R.E[g] + R.O[g];
+}
+__device__ __forceinline__ void right_shifted(const RowSet &R, uint32_t *orr)      // (p2,p4) of each group
+{
+#pragma unroll
+    for (int g = 0; g < 4; g++) orr[g] = g == 3 ? __byte_perm(R.E[3], R.LR, 0x7632) : __byte_perm(R.E[g], R.E[g + 1], 0x5432);
 }
 template <int JT>
-__device__ __forceinline__ void thumb_pairs_finish(Thumb<JT> &T, uint32_t info)
+__device__ __forceinline__ void thumb_pairs_begin(const Band &B, const Thumb<JT> &T, const uint32_t *XU, const uint32_t *XC, uint32_t *s0, uint32_t *s1)
 {
-    const uint32_t bw = (info >> 2) & 0xfffu;
-    uint32_t u[JT];
+    asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(B.slot), "r"(XU[0]), "r"(XU[1]), "r"(XU[2]), "r"(XU[3]) : "memory");
+    asm volatile("st.shared.v4.u32 [%0+16], {%1,%2,%3,%4};" ::"r"(B.slot), "r"(XC[0]), "r"(XC[1]), "r"(XC[2]), "r"(XC[3]) : "memory");
 #pragma unroll
     for (int k = 0; k < JT; k++) {
-        uint32_t sum;
-        asm volatile("ld.shared.u16 %0, [%1];" : "=r"(sum) : "r"(T.addr[k]) : "memory");
-        u[k] = (bw * sum) >> 10;             // (bw * ((1024 * sum) >> 4)) >> 16
+        asm volatile("ld.shared.u16 %0, [%1];" : "=r"(s0[k]) : "r"(T.addr[k]) : "memory");
+        asm volatile("ld.shared.u16 %0, [%1+16];" : "=r"(s1[k]) : "r"(T.addr[k]) : "memory");
     }
-    if (info & 2u) {
-        uint8_t *dst = T.dst + (size_t)(info >> 16) * AVD_T;
+}
+template <int JT>
+__device__ __forceinline__ void thumb_pairs_end(const Thumb<JT> &T, uint32_t info, const uint32_t *s0, const uint32_t *s1)
+{
+    const uint32_t b1 = (info >> 2) & 0xfffu, b0 = 2048u - b1;
+    uint8_t *dst = T.dst + (size_t)(info >> 16) * AVD_T;
 #pragma unroll
-        for (int k = 0; k < JT; k++)
-            if (k < T.ntx) dst[k] = (uint8_t)((T.u0[k] + u[k] + 2u) >> 2);
-    } else {
-#pragma unroll
-        for (int k = 0; k < JT; k++) T.u0[k] = u[k];
-    }
+    for (int k = 0; k < JT; k++)          // (b * ((1024 * sum) >> 4)) >> 16  ==  (b * sum) >> 10
+        if (k < T.ntx) dst[k] = (uint8_t)((((b0 * s0[k]) >> 10) + ((b1 * s1[k]) >> 10) + 2u) >> 2);
 }
 
 // Laplacian statistics of centre row C (rows above / below: U, D), its INTER_AREA column sums and, in the pair-sum
@@ -247,16 +255,14 @@ __device__ __forceinline__ void lap_step(const Band &B, const RowSet &U, const R
         orr[g] = g == 3 ? __byte_perm(C.E[3], C.LR, 0x7632) : __byte_perm(C.E[g], C.E[g + 1], 0x5432);
         Pp[g] = C.E[g] + C.O[g];
     }
+    uint32_t s0[JT], s1[JT];
 #if !K1_NOTHUMB
-    if (PAIR && (infoC & 1u)) {
-        if (B.todd) {
-            uint32_t Q[4];
-#pragma unroll
-            for (int g = 0; g < 4; g++) Q[g] = C.O[g] + orr[g];
-            thumb_pairs_store<JT>(B, Q);
-        } else {
-            thumb_pairs_store<JT>(B, Pp);
-        }
+    if (PAIR && (infoC & 2u)) {               // C is the bottom tap row of a thumbnail row, U its top tap row
+        uint32_t orrU[4], XU[4], XC[4];
+        right_shifted(U, orrU);
+        pair_sums(U, orrU, B.todd, XU);
+        pair_sums(C, orr, B.todd, XC);
+        thumb_pairs_begin<JT>(B, T, XU, XC, s0, s1);
     }
 #endif
 #pragma unroll
@@ -272,7 +278,7 @@ __device__ __forceinline__ void lap_step(const Band &B, const RowSet &U, const R
     }
     A.aLR += C.LR; A.aE0 += C.E[0]; A.aO3 += C.O[3];
 #if !K1_NOTHUMB
-    if (PAIR && (infoC & 1u)) thumb_pairs_finish<JT>(T, infoC);
+    if (PAIR && (infoC & 2u)) thumb_pairs_end<JT>(T, infoC, s0, s1);
 #endif
 }
 
@@ -544,15 +550,13 @@ __global__ void __launch_bounds__(MAXT, MINB) k1_fused_kernel(K1Params P)
     auto band_end = [&](const RowSet &C, const RowSet &D) {
 #if !K1_NOTHUMB && !K1_STUB
         const uint32_t infoD = row_info(nseq - 1);       // the bottom halo row is never a centre row
-        if (PAIR && (infoD & 1u)) {
-            uint32_t X[4];
-#pragma unroll
-            for (int g = 0; g < 4; g++) {
-                const uint32_t orr = g == 3 ? __byte_perm(D.E[3], D.LR, 0x7632) : __byte_perm(D.E[g], D.E[g + 1], 0x5432);
-                X[g] = B.todd ? D.O[g] + orr : D.E[g] + D.O[g];
-            }
-            thumb_pairs_store<JT>(B, X);
-            thumb_pairs_finish<JT>(T, infoD);
+        if (PAIR && (infoD & 2u)) {
+            uint32_t orrC[4], orrD[4], XU[4], XC[4], s0[JT], s1[JT];
+            right_shifted(C, orrC); right_shifted(D, orrD);
+            pair_sums(C, orrC, B.todd, XU);
+            pair_sums(D, orrD, B.todd, XC);
+            thumb_pairs_begin<JT>(B, T, XU, XC, s0, s1);
+            thumb_pairs_end<JT>(T, infoD, s0, s1);
         }
 #endif
         tv += (int)row_sum(D) - (int)row_sum(C);
@@ -630,7 +634,14 @@ __global__ void __launch_bounds__(MAXT, MINB) k1_fused_kernel(K1Params P)
         out = k + (d2 >= 0 ? 1u : 0u);
     }
     P.area32[(size_t)f * 1024 + b * 32 + lane] = (uint8_t)out;
-    P.areaflag[(size_t)f * 1024 + b * 32 + lane] = close ? 1 : 0;   // recomputed in the library's float32 order by k1_hash_finalize
+    // uncertified cells go to a list; k1_hash_finalize recomputes them in the library's float32 order
+    const uint32_t mask = __ballot_sync(0xffffffffu, close);
+    if (mask) {
+        uint32_t base = 0;
+        if (lane == 0) base = atomicAdd(P.fixlist, (uint32_t)__popc(mask));
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (close) P.fixlist[1 + base + __popc(mask & ((1u << lane) - 1u))] = (uint32_t)(P.frame0 + f) * 1024u + (uint32_t)(b * 32 + lane);
+    }
 }
 
 }  // namespace
@@ -667,7 +678,7 @@ static int k1_launch(avd_ctx *ctx, const K1Params &P, int n, size_t smem, int th
         K1Params Q = P;
         Q.bgr = P.bgr + (size_t)f0 * P.fstride; Q.rec = P.rec + f0;
         Q.thumbs = P.thumbs + (size_t)f0 * AVD_T * AVD_T; Q.area32 = P.area32 + (size_t)f0 * 1024;
-        Q.areaflag = P.areaflag + (size_t)f0 * 1024;
+        Q.frame0 = f0;
         AVD_LAUNCH(ctx, "k1_fused", st, (k1_fused_kernel<MAXT, MINB, JT, PAIR><<<dim3(AVD_D, nb), threads, smem, st>>>(Q)));
     }
     return AVD_OK;
@@ -675,18 +686,19 @@ static int k1_launch(avd_ctx *ctx, const K1Params &P, int n, size_t smem, int th
 
 int k1_fused(avd_ctx *ctx, const uint8_t *d_bgr, int n, int H, int W, size_t pitch, size_t fstride,
              const ShapeTables *tab, const ShapeTables *htab, avd_sample_rec *d_rec, uint8_t *d_thumbs,
-             uint8_t *d_area32, uint8_t *d_areaflag, cudaStream_t st)
+             uint8_t *d_area32, uint32_t *d_fixlist, cudaStream_t st)
 {
     K1Params P{};
     P.bgr = d_bgr; P.pitch = pitch; P.fstride = fstride; P.H = H; P.W = W; P.row_bytes = 3 * W;
-    P.tab = tab; P.rec = d_rec; P.thumbs = d_thumbs; P.area32 = d_area32; P.areaflag = d_areaflag;
+    P.tab = tab; P.rec = d_rec; P.thumbs = d_thumbs; P.area32 = d_area32; P.fixlist = d_fixlist;
     const size_t smem = k1_smem_bytes(W);
     const int threads = (W / 16 + 31) / 32 * 32;
     const int jt = htab->strip_ntx_max;
     // pair-sum thumbnail: every horizontal tap pair is (1024, 1024) and all left taps have the same parity
     bool pair = true;
     for (int i = 0; i < AVD_T; i++)
-        if (htab->lx[i].a0 != 1024 || htab->lx[i].a1 != 1024 || ((htab->lx[i].i0 ^ htab->lx[0].i0) & 1)) pair = false;
+        if (htab->lx[i].a0 != 1024 || htab->lx[i].a1 != 1024 || ((htab->lx[i].i0 ^ htab->lx[0].i0) & 1) ||
+            htab->ly[i].a0 + htab->ly[i].a1 != 2048) pair = false;
     if (threads <= 128) {                                            // <= 2048 px wide
         if (pair) {
             if (jt <= 3) return k1_launch<128, K1_MINB, 3, true>(ctx, P, n, smem, threads, st);

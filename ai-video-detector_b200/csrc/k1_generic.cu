@@ -11,9 +11,10 @@
 
 namespace {
 
-__global__ void rec_init_kernel(avd_sample_rec *rec, int n)
+__global__ void rec_init_kernel(avd_sample_rec *rec, int n, uint32_t *fixcount)
 {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i == 0 && fixcount) *fixcount = 0;
     if (i >= n) return;
     rec[i].lap_sum = 0; rec[i].lap_sumsq = 0; rec[i].flow_mean = 0.f; rec[i].flow_var = 0.f;
     rec[i].ham_prev = -1; rec[i].flags = 0;
@@ -129,58 +130,51 @@ __global__ void thumb_kernel(const uint8_t *__restrict__ gray, int H, int W, con
 }
 
 // INTER_AREA cells the streaming kernel could not certify (exact mean too close to a rounding boundary, ~0.2 % of
-// cells): recomputed here in the library's exact float32 order.  One CTA per frame; all threads
-// produce the weighted pixels fl(g * alpha) of a cell in parallel, then only the float32 additions -- whose order is
-// what matters -- run as sequential chains (one thread per source row, then one thread over the rows).
-constexpr int FIX_FLOATS = 8192;
-__global__ void __launch_bounds__(1024) area_fix_kernel(K1FixArgs A, uint8_t *__restrict__ area32)
+// cells): recomputed here in the library's exact float32 order.  The CTAs share the list; all threads
+// of a CTA produce the weighted pixels fl(g * alpha) of a cell in parallel, then only the float32 additions -- whose
+// order is what matters -- run as sequential chains (one thread per source row, then one thread over the rows).
+constexpr int FIX_FLOATS = 8192, FIX_THREADS = 256;
+__global__ void __launch_bounds__(FIX_THREADS) area_fix_kernel(K1FixArgs A, uint8_t *__restrict__ area32)
 {
-    __shared__ uint32_t masks[32];
     __shared__ float prod[FIX_FLOATS];
-    __shared__ float tv[256];
-    const int f = blockIdx.x, tid = threadIdx.x;
-    const uint32_t m = __ballot_sync(0xffffffffu, A.flags[(size_t)f * 1024 + tid] != 0);
-    if ((tid & 31) == 0) masks[tid >> 5] = m;
-    __syncthreads();
-    const uint8_t *frame = A.bgr + (size_t)f * A.fstride;
-    for (int dy = 0; dy < 32; dy++) {
-        uint32_t mm = masks[dy];
-        if (!mm) continue;
-        const AreaCell cy = A.tab->ay[dy];
+    __shared__ float tv[FIX_THREADS];
+    const int tid = threadIdx.x;
+    const uint32_t count = A.list[0];
+    for (uint32_t e = blockIdx.x; e < count; e += gridDim.x) {
+        const uint32_t ent = A.list[1 + e];
+        const int f = (int)(ent >> 10), dy = (int)((ent >> 5) & 31u), dx = (int)(ent & 31u);
+        const uint8_t *frame = A.bgr + (size_t)f * A.fstride;
+        const AreaCell cy = A.tab->ay[dy], cx = A.tab->ax[dx];
         const int r0 = cy.has_head ? cy.s1 - 1 : cy.s1, r1 = cy.has_tail ? cy.s2 : cy.s2 - 1, nr = r1 - r0 + 1;
-        while (mm) {
-            const int dx = __ffs(mm) - 1;
-            mm &= mm - 1;
-            const AreaCell cx = A.tab->ax[dx];
-            const int x0 = cx.has_head ? cx.s1 - 1 : cx.s1, x1 = cx.has_tail ? cx.s2 : cx.s2 - 1, nc = x1 - x0 + 1;
-            int ch = FIX_FLOATS / nc;
-            if (ch > 256) ch = 256;
-            float sum = 0.f;
-            for (int rb = 0; rb < nr; rb += ch) {
-                const int cnt = min(ch, nr - rb);
-                for (int idx = tid; idx < cnt * nc; idx += 1024) {
-                    const int r = idx / nc, c = idx - r * nc;
-                    const uint8_t *px = frame + (size_t)(r0 + rb + r) * A.pitch + 3 * (size_t)(x0 + c);
-                    const float g = (float)((3735u * px[0] + 19235u * px[1] + 9798u * px[2] + 16384u) >> 15);
-                    const float w = (cx.has_head && c == 0) ? cx.ah : ((cx.has_tail && c == nc - 1) ? cx.at : cx.am);
-                    prod[idx] = __fmul_rn(g, w);
-                }
-                __syncthreads();
-                if (tid < cnt) {
-                    const float *pr = prod + tid * nc;
-                    float buf = 0.f;
-                    for (int i = 0; i < nc; i++) buf = __fadd_rn(buf, pr[i]);
-                    const int row = r0 + rb + tid;
-                    const float beta = (cy.has_head && row == r0) ? cy.ah : ((cy.has_tail && row == cy.s2) ? cy.at : cy.am);
-                    tv[tid] = __fmul_rn(beta, buf);
-                }
-                __syncthreads();
-                if (tid == 0)
-                    for (int i = 0; i < cnt; i++) sum = __fadd_rn(sum, tv[i]);
-                __syncthreads();
+        const int x0 = cx.has_head ? cx.s1 - 1 : cx.s1, x1 = cx.has_tail ? cx.s2 : cx.s2 - 1, nc = x1 - x0 + 1;
+        int ch = FIX_FLOATS / nc;
+        if (ch > FIX_THREADS) ch = FIX_THREADS;
+        float sum = 0.f;
+        for (int rb = 0; rb < nr; rb += ch) {
+            const int cnt = min(ch, nr - rb);
+            for (int idx = tid; idx < cnt * nc; idx += FIX_THREADS) {
+                const int r = idx / nc, c = idx - r * nc;
+                const uint8_t *px = frame + (size_t)(r0 + rb + r) * A.pitch + 3 * (size_t)(x0 + c);
+                const float g = (float)((3735u * px[0] + 19235u * px[1] + 9798u * px[2] + 16384u) >> 15);
+                const float w = (cx.has_head && c == 0) ? cx.ah : ((cx.has_tail && c == nc - 1) ? cx.at : cx.am);
+                prod[idx] = __fmul_rn(g, w);
             }
-            if (tid == 0) area32[(size_t)f * 1024 + dy * 32 + dx] = sat_rne(sum);
+            __syncthreads();
+            if (tid < cnt) {
+                const float *pr = prod + tid * nc;
+                float buf = 0.f;
+#pragma unroll 4
+                for (int i = 0; i < nc; i++) buf = __fadd_rn(buf, pr[i]);
+                const int row = r0 + rb + tid;
+                const float beta = (cy.has_head && row == r0) ? cy.ah : ((cy.has_tail && row == cy.s2) ? cy.at : cy.am);
+                tv[tid] = __fmul_rn(beta, buf);
+            }
+            __syncthreads();
+            if (tid == 0)
+                for (int i = 0; i < cnt; i++) sum = __fadd_rn(sum, tv[i]);
+            __syncthreads();
         }
+        if (tid == 0) area32[(size_t)f * 1024 + dy * 32 + dx] = sat_rne(sum);
     }
 }
 
@@ -225,16 +219,16 @@ __global__ void hash_kernel(const uint8_t *__restrict__ area32, const uint32_t *
 
 }  // namespace
 
-int k1_rec_init(avd_ctx *ctx, avd_sample_rec *d_rec, int n, cudaStream_t st)
+int k1_rec_init(avd_ctx *ctx, avd_sample_rec *d_rec, int n, uint32_t *d_fixcount, cudaStream_t st)
 {
-    AVD_LAUNCH(ctx, "rec_init", st, rec_init_kernel<<<(n + 255) / 256, 256, 0, st>>>(d_rec, n));
+    AVD_LAUNCH(ctx, "rec_init", st, rec_init_kernel<<<(n + 255) / 256, 256, 0, st>>>(d_rec, n, d_fixcount));
     return AVD_OK;
 }
 
 int k1_hash_finalize(avd_ctx *ctx, uint8_t *d_area32, int n, const uint32_t *d_prev_hash,
                      avd_sample_rec *d_rec, const K1FixArgs *fix, cudaStream_t st)
 {
-    if (fix) AVD_LAUNCH(ctx, "area_fix", st, area_fix_kernel<<<n, 1024, 0, st>>>(*fix, d_area32));
+    if (fix) AVD_LAUNCH(ctx, "area_fix", st, area_fix_kernel<<<2 * ctx->sm_count, FIX_THREADS, 0, st>>>(*fix, d_area32));
     AVD_LAUNCH(ctx, "hash", st, hash_kernel<<<n, 1024, 0, st>>>(d_area32, d_prev_hash, d_rec));
     return AVD_OK;
 }
