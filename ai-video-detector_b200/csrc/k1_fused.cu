@@ -65,6 +65,7 @@ constexpr int NRS = K1_NRS;           // single-row TMA stages per CTA (multiple
 static_assert(NRS % 3 == 0 && NRS <= 6, "stages come in groups of 3: the position inside a group is tied to the 3-way register rotation");
 constexpr int NGRP = NRS / 3;
 constexpr int MAXQ = 132;             // rows a band can load (H/32 + 3, H <= 4096)
+constexpr int MAX_TROWS = 16;         // thumbnail rows a band can own (staged in shared memory, pair form)
 constexpr int SLOT = 48;              // bytes of a thread's private gray slot (48: conflict-free 128-bit stores)
 
 // shared-memory header (bytes)
@@ -198,7 +199,8 @@ struct Band {
 template <int JT> struct Thumb {
     uint32_t addr[JT], a0[JT], a1[JT], u0[JT];
     int ntx;
-    uint8_t *dst;                          // &thumbs[frame][0][first column of this thread]
+    uint8_t *dst;                          // &thumbs[frame][0][first column of this thread] (general form)
+    uint32_t th;                           // pair form: shared address of this thread's first column in the band's staged rows
 };
 
 // ---- thumbnail, pair-sum form (W a multiple of 640: every horizontal tap pair has weights 1024/1024, so the
@@ -232,10 +234,12 @@ template <int JT>
 __device__ __forceinline__ void thumb_pairs_end(const Thumb<JT> &T, uint32_t info, const uint32_t *s0, const uint32_t *s1)
 {
     const uint32_t b1 = (info >> 2) & 0xfffu, b0 = 2048u - b1;
-    uint8_t *dst = T.dst + (size_t)(info >> 16) * AVD_T;
+    const uint32_t row = T.th + (info >> 16) * AVD_T;          // the band's thumbnail rows are staged in shared memory
 #pragma unroll
-    for (int k = 0; k < JT; k++)          // (b * ((1024 * sum) >> 4)) >> 16  ==  (b * sum) >> 10
-        if (k < T.ntx) dst[k] = (uint8_t)((((b0 * s0[k]) >> 10) + ((b1 * s1[k]) >> 10) + 2u) >> 2);
+    for (int k = 0; k < JT; k++) {        // (b * ((1024 * sum) >> 4)) >> 16  ==  (b * sum) >> 10
+        const uint32_t v = (((b0 * s0[k]) >> 10) + ((b1 * s1[k]) >> 10) + 2u) >> 2;
+        if (k < T.ntx) asm volatile("st.shared.u8 [%0], %1;" ::"r"(row + k), "r"(v) : "memory");
+    }
 }
 
 // Laplacian statistics of centre row C (rows above / below: U, D), its INTER_AREA column sums and, in the pair-sum
@@ -496,6 +500,7 @@ __global__ void __launch_bounds__(MAXT, MINB) k1_fused_kernel(K1Params P)
         const int tx0 = tab->strip_tx0[tid];
         T.ntx = 16 * tid < W ? tab->strip_ntx[tid] : 0;
         T.dst = P.thumbs + (size_t)f * AVD_T * AVD_T + tx0;
+        T.th = B.slot - SLOT * tid + SLOT * nthr + 64 + tx0 - (uint32_t)(tab->thumb_row_begin[b] * AVD_T);   // row index comes as an absolute thumbnail row
 #pragma unroll
         for (int k = 0; k < JT; k++) {
             const LinTap t = tab->lx[min(tx0 + k, AVD_T - 1)];
@@ -618,7 +623,14 @@ __global__ void __launch_bounds__(MAXT, MINB) k1_fused_kernel(K1Params P)
     is_last = __shfl_sync(0xffffffffu, is_last, 0);
     if (!is_last) return;
 
-    // ---- INTER_AREA destination row b, column `lane` (this warp is the last one of the band) ----
+    // ---- this warp is the last one of the band: the staged thumbnail rows (contiguous in the thumbnail) go out ----
+    if (PAIR) {
+        const int ty0 = tab->thumb_row_begin[b], nty = tab->thumb_row_begin[b + 1] - ty0;
+        const uint4 *src = (const uint4 *)(smem + HDR + NRS * P.row_bytes + 64 + SLOT * nthr + 64);
+        uint4 *dst = (uint4 *)(P.thumbs + ((size_t)f * AVD_T + ty0) * AVD_T);
+        for (int i = lane; i < nty * (AVD_T / 16); i += 32) dst[i] = src[i];
+    }
+    // ---- INTER_AREA destination row b, column `lane` ----
     const int M = cellM[lane];
     uint32_t out;
     bool close = false;
@@ -649,7 +661,7 @@ __global__ void __launch_bounds__(MAXT, MINB) k1_fused_kernel(K1Params P)
 static size_t k1_smem_bytes(int W)
 {
     const int nthr = (W / 16 + 31) / 32 * 32;
-    return HDR + (size_t)NRS * 3 * W + 64 + (size_t)SLOT * nthr + 64;
+    return HDR + (size_t)NRS * 3 * W + 64 + (size_t)SLOT * nthr + 64 + (size_t)MAX_TROWS * AVD_T;
 }
 
 bool k1_fused_supported(int H, int W, size_t pitch, size_t fstride, const void *base, const ShapeTables *htab)
@@ -657,6 +669,8 @@ bool k1_fused_supported(int H, int W, size_t pitch, size_t fstride, const void *
     if (W % 64 != 0 || W < 1280 || W > 4096 || H < 640 || H > 4096 || htab->thumb_2x2) return false;
     if (pitch % 16 != 0 || fstride % 16 != 0 || ((uintptr_t)base % 16) != 0) return false;
     if (k1_smem_bytes(W) > 227 * 1024 || htab->strip_ntx_max > 4) return false;
+    for (int b = 0; b < AVD_D; b++)
+        if (htab->thumb_row_begin[b + 1] - htab->thumb_row_begin[b] > MAX_TROWS) return false;
     // plain two-tap decimation: taps (i, i+1), every tap row used by exactly one thumbnail row
     for (int i = 0; i < AVD_T; i++) {
         if (htab->lx[i].i1 != htab->lx[i].i0 + 1 || htab->ly[i].i1 != htab->ly[i].i0 + 1) return false;
