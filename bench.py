@@ -54,6 +54,17 @@ def make_frames(rank: int, world: int, out: np.ndarray, halo_out):
         halo_out[...] = clip[(first - 1) * STEP]
 
 
+def k1_traffic(frames_per_launch):
+    """DRAM bytes per K1 launch from the committed ncu capture (profiles/r01_k1_traffic.json), scaled per frame."""
+    p = os.path.join(ROOT, "profiles", "r01_k1_traffic.json")
+    if not os.path.exists(p):
+        return None
+    d = json.load(open(p))
+    if (d["H"], d["W"]) != (H, W):
+        return None
+    return (d["dram_bytes_read"] + d["dram_bytes_write"]) / d["frames_per_launch"] * frames_per_launch
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -280,7 +291,8 @@ def main():
             "e2e": {"value": n_total * args.steps / dt_e2e, "unit": "frames/s", "h2d_bytes_per_step": int(FRAME_BYTES * (SAMPLES * world + world - 1)),
                     "d2h_bytes_per_step": int(160 * n_total), "ms_per_step": 1e3 * dt_e2e / args.steps},
             "roofline": {"kernel": k1_name, "bound": "hbm", "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm,
-                         "traffic": None, "peak_source": hbm_src, "ms_per_launch": k1_ms, "frames_per_launch": frames_per_launch,
+                         "traffic": k1_traffic(frames_per_launch) if k1_name == "k1_fused" else None,
+                         "traffic_source": "ncu --set full, dram__bytes_read+write per launch (profiles/r01_k1_traffic.json)", "peak_source": hbm_src, "ms_per_launch": k1_ms, "frames_per_launch": frames_per_launch,
                          "share_of_kernel_time": k1["ms"] / total_kernel_ms if total_kernel_ms else None},
             "kernels": {k: {"ms_per_step": v["ms"] / args.steps, "launches_per_step": v["launches"] / args.steps} for k, v in sorted(kern.items())},
             "k2_us_per_pair": 1e3 * sum(v["ms"] for k, v in kern.items() if k in ("pyr", "polyexp", "update_matrices", "box_solve", "magstats")) / args.steps / (SAMPLES - (0 if d_halo is not None else 1)),
