@@ -12,6 +12,7 @@
 #include "avd_internal.h"
 #include <math.h>
 #include <stdlib.h>
+#include <stdio.h>
 
 namespace {
 
@@ -255,9 +256,12 @@ __global__ void __launch_bounds__(256) update_matrices_kernel(const float *__res
 // shuffles of per-lane partial sums: window(j) = [T(t-1)+T(t)+T(t+1)] + suffix_{t-2}(j+1) + prefix_{t+2}(j).
 // float64 sums of <=225 float32 values are exact to ~1e-16, so any summation order agrees with the library's.
 // STATS: the last iteration of the finest level also emits per-task sums of |flow| and |flow|^2.
-constexpr int BX_SEG = 32, BX_COLS = 112, BX_WARPS = 4, BS_M = 7;
+// The segment length trades redundant window start-up (15 rows per segment) for parallelism: the small pyramid levels
+// are latency-bound (a few hundred warps for the whole GPU), so they use short segments.
+constexpr int BX_COLS = 112, BX_WARPS = 4, BS_M = 7;
+constexpr int BX_MIN_SEG = 8;
 __host__ __device__ constexpr int bx_strips(int s) { return (s + BX_COLS - 1) / BX_COLS; }
-__host__ __device__ constexpr int bx_segs(int s) { return (s + BX_SEG - 1) / BX_SEG; }
+__host__ __device__ constexpr int bx_segs(int s, int seg) { return (s + seg - 1) / seg; }
 
 __device__ __forceinline__ float4 ld_row4(const float *__restrict__ rowp, int xa, int xb, int s)
 {
@@ -277,12 +281,12 @@ __device__ __forceinline__ float4 ld_row4(const float *__restrict__ rowp, int xa
 }
 
 template <bool STATS>
-__global__ void __launch_bounds__(32 * BX_WARPS) box_solve_kernel(const float *__restrict__ Mall, float *__restrict__ flow, int k,
+__global__ void __launch_bounds__(32 * BX_WARPS) box_solve_kernel(const float *__restrict__ Mall, float *__restrict__ flow, int k, int BX_SEG,
                                                                  int n_pairs, double *__restrict__ task_stats, int p_base)
 {
     const int s = lvl_size(k);
     const int lane = threadIdx.x & 31;
-    const int tasks_per_pair = bx_strips(s) * bx_segs(s);
+    const int tasks_per_pair = bx_strips(s) * bx_segs(s, BX_SEG);
     const int task = blockIdx.x * BX_WARPS + (threadIdx.x >> 5);
     if (task >= tasks_per_pair * n_pairs) return;
     const int pl = task / tasks_per_pair, tp = task - pl * tasks_per_pair, p = pl + p_base;
@@ -449,10 +453,10 @@ FlowConst make_consts()
 
 // Workspace per batch of NI images / NP pairs (floats):
 //   pyr  NI*136000 | R  NI*136000*5 | M  NP*5*320*320 | flowA, flowB  NP*2*320*320 each | tile stats NP*100*2 doubles
-constexpr int STAT_TILES = bx_strips(T) * bx_segs(T);    // tasks per pair at the finest level
+constexpr int STAT_TILES_MAX = bx_strips(T) * bx_segs(T, BX_MIN_SEG);    // most tasks per pair at the finest level
 static size_t k2_ws_bytes(int ni, int np)
 {
-    return sizeof(float) * ((size_t)ni * PYR_PX * 6 + (size_t)np * T * T * 9) + sizeof(double) * 2 * STAT_TILES * (size_t)np;
+    return sizeof(float) * ((size_t)ni * PYR_PX * 6 + (size_t)np * T * T * 9) + sizeof(double) * 2 * STAT_TILES_MAX * (size_t)np;
 }
 
 int k2_flow(avd_ctx *ctx, const uint8_t *d_prev, const uint8_t *d_next, size_t prev_stride, size_t next_stride,
@@ -500,6 +504,14 @@ int k2_flow(avd_ctx *ctx, const uint8_t *d_prev, const uint8_t *d_next, size_t p
         // Optional L2-resident sub-batching of levels 0/1 (AVD_K2_SB0 / AVD_K2_SB1 = pairs per sub-batch, 0 = off).
         // Measured on B200 (profiles/r01_k2_notes.md): OFF is faster -- box_solve has only 30 warps of work per pair,
         // so a 16-pair sub-batch leaves most SMs idle (box_solve 1.06 -> 4.1 ms, update_matrices 0.69 -> 0.84 ms).
+        // rows per box_solve segment, per level (AVD_K2_SEG="s0,s1,s2,s3" overrides; multiples of 8)
+        static int seg_rows[4] = {64, 16, 8, 8};
+        static bool seg_init = false;
+        if (!seg_init) {
+            if (const char *e = getenv("AVD_K2_SEG")) sscanf(e, "%d,%d,%d,%d", &seg_rows[0], &seg_rows[1], &seg_rows[2], &seg_rows[3]);
+            for (int &v : seg_rows) v = v < BX_MIN_SEG ? BX_MIN_SEG : v;
+            seg_init = true;
+        }
         static int sb0 = getenv("AVD_K2_SB0") ? atoi(getenv("AVD_K2_SB0")) : 0, sb1 = getenv("AVD_K2_SB1") ? atoi(getenv("AVD_K2_SB1")) : 0;
         for (int k = 3; k >= 0; k--) {
             const int s = lvl_size(k);
@@ -507,7 +519,8 @@ int k2_flow(avd_ctx *ctx, const uint8_t *d_prev, const uint8_t *d_next, size_t p
             for (int q0 = 0; q0 < np; q0 += SB) {
                 const int nq = np - q0 < SB ? np - q0 : SB;
                 dim3 gu((s + 31) / 32, (s + 7) / 8, nq), bu(32, 8);
-                const int bx_blocks = (bx_strips(s) * bx_segs(s) * nq + BX_WARPS - 1) / BX_WARPS;
+                const int seg = seg_rows[k];
+                const int bx_blocks = (bx_strips(s) * bx_segs(s, seg) * nq + BX_WARPS - 1) / BX_WARPS;
                 if (k == 3) {
                     AVD_LAUNCH(ctx, "update_matrices", st, update_matrices_kernel<0><<<gu, bu, 0, st>>>(R, nullptr, nullptr, M, nullptr, k, mode, q0));
                 } else {
@@ -515,9 +528,9 @@ int k2_flow(avd_ctx *ctx, const uint8_t *d_prev, const uint8_t *d_next, size_t p
                 }
                 for (int it = 0; it < 3; it++) {
                     if (k == 0 && it == 2 && d_rec_first) {
-                        AVD_LAUNCH(ctx, "box_solve", st, box_solve_kernel<true><<<bx_blocks, 32 * BX_WARPS, 0, st>>>(M, cur, k, nq, tile_stats, q0));
+                        AVD_LAUNCH(ctx, "box_solve", st, box_solve_kernel<true><<<bx_blocks, 32 * BX_WARPS, 0, st>>>(M, cur, k, seg, nq, tile_stats, q0));
                     } else {
-                        AVD_LAUNCH(ctx, "box_solve", st, box_solve_kernel<false><<<bx_blocks, 32 * BX_WARPS, 0, st>>>(M, cur, k, nq, nullptr, q0));
+                        AVD_LAUNCH(ctx, "box_solve", st, box_solve_kernel<false><<<bx_blocks, 32 * BX_WARPS, 0, st>>>(M, cur, k, seg, nq, nullptr, q0));
                     }
                     if (it < 2) {
                         AVD_LAUNCH(ctx, "update_matrices", st, update_matrices_kernel<1><<<gu, bu, 0, st>>>(R, cur, nullptr, M, nullptr, k, mode, q0));
@@ -528,7 +541,7 @@ int k2_flow(avd_ctx *ctx, const uint8_t *d_prev, const uint8_t *d_next, size_t p
         }
         if (d_rec_first) {
             // chain: pair p0+j -> record of its "next" image
-            AVD_LAUNCH(ctx, "magstats", st, magstats_finalize_kernel<<<(np + 127) / 128, 128, 0, st>>>(tile_stats, STAT_TILES, d_rec_first + p0, np));
+            AVD_LAUNCH(ctx, "magstats", st, magstats_finalize_kernel<<<(np + 127) / 128, 128, 0, st>>>(tile_stats, bx_strips(T) * bx_segs(T, seg_rows[0]), d_rec_first + p0, np));
         }
         if (d_flow_out) {
             size_t total = (size_t)np * T * T;

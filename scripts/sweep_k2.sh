@@ -1,4 +1,4 @@
 #!/bin/bash
-# K2 sub-batch sweep: scripts/sweep_k2.sh n reps
+# box_solve segment-length sweep: scripts/sweep_k2.sh "32,16,8,8" "16,8,8,8" ...
 cd "$(dirname "$0")/.."
-for sb in "0 0" "8 48" "12 48" "16 48" "24 64" "12 0"; do set -- $sb; echo -n "SB0=$1 SB1=$2: "; AVD_K2_SB0=$1 AVD_K2_SB1=$2 python scripts/prof_k2.py 120 3 | tail -1; done
+for s in "$@"; do echo -n "SEG=$s: "; AVD_K2_SEG=$s python scripts/prof_k2.py 120 5 | tail -1; done
