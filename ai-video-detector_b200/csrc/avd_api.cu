@@ -3,6 +3,7 @@
 #include <math.h>
 #include <string.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <new>
 #include <memory>
 #include <vector>
@@ -360,7 +361,8 @@ int avd_analyze_host(avd_ctx *ctx, const uint8_t *const *h_frames, int n, int H,
     const int SLOTS = 3;
     int per_slot = (int)((48u << 20) / fbytes);
     if (per_slot < 1) per_slot = 1;
-    if (per_slot > 16) per_slot = 16;
+    static const int max_slot = getenv("AVD_HOST_CHUNK") ? atoi(getenv("AVD_HOST_CHUNK")) : 16;   // frames per device slot (tuning)
+    if (per_slot > max_slot) per_slot = max_slot < 1 ? 1 : max_slot;
     if (per_slot > n) per_slot = n;
     if ((rc = avd_ensure(ctx, (void **)&ctx->ring, &ctx->ring_cap, (size_t)SLOTS * per_slot * fbytes))) return rc;
     if ((rc = avd_ensure(ctx, (void **)&ctx->thumbs, &ctx->thumbs_cap, (size_t)n * AVD_T * AVD_T))) return rc;
