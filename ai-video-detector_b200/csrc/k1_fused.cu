@@ -31,6 +31,8 @@
 // round(mean).  The few cells (~0.2 %) that are closer are listed and recomputed in the library's exact float32
 // order by area_fix_kernel (k1_generic.cu), off this kernel's critical path.
 #include "avd_internal.h"
+#include <stdio.h>
+#include <stdlib.h>
 
 namespace {
 
@@ -230,6 +232,18 @@ __device__ __forceinline__ void thumb_pairs_begin(const Band &B, const Thumb<JT>
         asm volatile("ld.shared.u16 %0, [%1+16];" : "=r"(s1[k]) : "r"(T.addr[k]) : "memory");
     }
 }
+// W = 1280 (TM 4) and W = 2560 (TM 8): the tap pairs sit at the same offsets in every strip (4g+1 resp. 3 and 11), so
+// the lanes come straight out of the registers, no trip through the slot
+template <int JT, int TM>
+__device__ __forceinline__ void thumb_pairs_static(const uint32_t *XU, const uint32_t *XC, uint32_t *s0, uint32_t *s1)
+{
+#pragma unroll
+    for (int k = 0; k < JT; k++) {
+        if (TM == 4) { s0[k] = XU[k & 3] & 0xffffu; s1[k] = XC[k & 3] & 0xffffu; }            // pair (4k+1, 4k+2): low lane of group k
+        else { s0[k] = XU[(2 * k) & 3] >> 16; s1[k] = XC[(2 * k) & 3] >> 16; }               // pair (8k+3, 8k+4): high lane of group 2k
+    }
+}
+
 template <int JT>
 __device__ __forceinline__ void thumb_pairs_end(const Thumb<JT> &T, uint32_t info, const uint32_t *s0, const uint32_t *s1)
 {
@@ -244,7 +258,7 @@ __device__ __forceinline__ void thumb_pairs_end(const Thumb<JT> &T, uint32_t inf
 
 // Laplacian statistics of centre row C (rows above / below: U, D), its INTER_AREA column sums and, in the pair-sum
 // form of the thumbnail, its thumbnail columns (infoC = thumbnail role of the centre row)
-template <int JT, bool PAIR>
+template <int JT, int TM>
 __device__ __forceinline__ void lap_step(const Band &B, const RowSet &U, const RowSet &C, const RowSet &D, Acc &A, Thumb<JT> &T, uint32_t infoC)
 {
 #if K1_STUB
@@ -261,12 +275,13 @@ __device__ __forceinline__ void lap_step(const Band &B, const RowSet &U, const R
     }
     uint32_t s0[JT], s1[JT];
 #if !K1_NOTHUMB
-    if (PAIR && (infoC & 2u)) {               // C is the bottom tap row of a thumbnail row, U its top tap row
+    if ((TM != 0) && (infoC & 2u)) {               // C is the bottom tap row of a thumbnail row, U its top tap row
         uint32_t orrU[4], XU[4], XC[4];
         right_shifted(U, orrU);
         pair_sums(U, orrU, B.todd, XU);
         pair_sums(C, orr, B.todd, XC);
-        thumb_pairs_begin<JT>(B, T, XU, XC, s0, s1);
+        if constexpr (TM >= 4) thumb_pairs_static<JT, TM>(XU, XC, s0, s1);
+        else thumb_pairs_begin<JT>(B, T, XU, XC, s0, s1);
     }
 #endif
 #pragma unroll
@@ -282,7 +297,7 @@ __device__ __forceinline__ void lap_step(const Band &B, const RowSet &U, const R
     }
     A.aLR += C.LR; A.aE0 += C.E[0]; A.aO3 += C.O[3];
 #if !K1_NOTHUMB
-    if (PAIR && (infoC & 2u)) thumb_pairs_end<JT>(T, infoC, s0, s1);
+    if ((TM != 0) && (infoC & 2u)) thumb_pairs_end<JT>(T, infoC, s0, s1);
 #endif
 }
 
@@ -329,7 +344,7 @@ __device__ K1_ISSUE_INLINE void issue_row(uint32_t sbase, int q, int s)
 // Stage s holds sequence row q: convert this thread's strip to gray (row set R); on tap rows of the thumbnail also
 // advance this thread's thumbnail columns.  Returns 1 in lane 0 of the warp that was last to leave the stage
 // (passed on to release_finish).
-template <int POS, int JT, bool PAIR>
+template <int POS, int JT, int TM>
 __device__ __forceinline__ uint32_t load_row(const Band &B, int q, int grp, uint32_t parity, uint32_t &ok, uint32_t nbar, uint32_t npar,
                                              int tid, bool first, bool last, RowSet &R, Thumb<JT> &T)
 {
@@ -376,11 +391,11 @@ __device__ __forceinline__ uint32_t load_row(const Band &B, int q, int grp, uint
     // general form of the thumbnail (any tap weights): handled when the row is loaded
     // info: bit0 tap, bit1 second row of its pair, bits 2-13 vertical weight, bits 16-24 thumbnail row
     uint32_t info = 0;
-    if (!PAIR) asm volatile("ld.shared.u32 %0, [%1];" : "=r"(info) : "r"(B.sbase + OFF_INFO + 4 * q));
+    if (!(TM != 0)) asm volatile("ld.shared.u32 %0, [%1];" : "=r"(info) : "r"(B.sbase + OFF_INFO + 4 * q));
 #if K1_NOTHUMB
     info = 0;                                 // timing experiment only
 #endif
-    if (!PAIR && (info & 1u)) {
+    if (!(TM != 0) && (info & 1u)) {
         uint4 gw;
         gw.x = __byte_perm(R.E[0], R.O[0], 0x6240); gw.y = __byte_perm(R.E[1], R.O[1], 0x6240);
         gw.z = __byte_perm(R.E[2], R.O[2], 0x6240); gw.w = __byte_perm(R.E[3], R.O[3], 0x6240);
@@ -435,7 +450,7 @@ __device__ __forceinline__ uint32_t masked_sum(const uint32_t *P, const uint32_t
     return s;
 }
 
-template <int MAXT, int MINB, int JT, bool PAIR>
+template <int MAXT, int MINB, int JT, int TM>
 __global__ void __launch_bounds__(MAXT, MINB) k1_fused_kernel(K1Params P)
 {
     extern __shared__ __align__(128) uint8_t smem[];
@@ -506,7 +521,7 @@ __global__ void __launch_bounds__(MAXT, MINB) k1_fused_kernel(K1Params P)
             const LinTap t = tab->lx[min(tx0 + k, AVD_T - 1)];
             const bool ok = k < T.ntx;
             const int rel = t.i0 - 16 * tid;                            // left tap, relative to the strip
-            T.addr[k] = B.slot + (ok ? (uint32_t)(PAIR ? 2 * (rel >> 1) : rel) : 0u);   // pair form: 16-bit lane rel/2 (even) or (rel-1)/2 (odd)
+            T.addr[k] = B.slot + (ok ? (uint32_t)((TM != 0) ? 2 * (rel >> 1) : rel) : 0u);   // pair form: 16-bit lane rel/2 (even) or (rel-1)/2 (odd)
             T.a0[k] = (uint32_t)t.a0; T.a1[k] = (uint32_t)t.a1; T.u0[k] = 0;
         }
     }
@@ -532,9 +547,9 @@ __global__ void __launch_bounds__(MAXT, MINB) k1_fused_kernel(K1Params P)
     uint32_t par = 0;
     int grp = 0;
     uint32_t ok = mbar_try(full_bar(0), 0u);
-    uint32_t t0 = load_row<0, JT, PAIR>(B, 0, 0, 0u, ok, full_bar(1), 0u, tid, first, last, R0, T);
+    uint32_t t0 = load_row<0, JT, TM>(B, 0, 0, 0u, ok, full_bar(1), 0u, tid, first, last, R0, T);
     release_finish<0>(B, 0, 0, t0);
-    uint32_t t1 = load_row<1, JT, PAIR>(B, 1, 0, 0u, ok, full_bar(2), 0u, tid, first, last, R1, T);
+    uint32_t t1 = load_row<1, JT, TM>(B, 1, 0, 0u, ok, full_bar(2), 0u, tid, first, last, R1, T);
     release_finish<1>(B, 1, 0, t1);
     int tv = (int)row_sum(R0) - (int)row_sum(R1);         // vertical part of sum L telescopes to 4 rows per band
     int mcA = 0, mcB = 0;                                  // cell sums in 1/32 units
@@ -549,18 +564,19 @@ __global__ void __launch_bounds__(MAXT, MINB) k1_fused_kernel(K1Params P)
     // thumbnail role of sequence row q (pair-sum form: looked up when the row is the centre row)
     auto row_info = [&](int qq) {
         uint32_t v = 0;
-        if (PAIR) asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(sbase + OFF_INFO + 4 * qq));
+        if ((TM != 0)) asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(sbase + OFF_INFO + 4 * qq));
         return v;
     };
     auto band_end = [&](const RowSet &C, const RowSet &D) {
 #if !K1_NOTHUMB && !K1_STUB
         const uint32_t infoD = row_info(nseq - 1);       // the bottom halo row is never a centre row
-        if (PAIR && (infoD & 2u)) {
+        if ((TM != 0) && (infoD & 2u)) {
             uint32_t orrC[4], orrD[4], XU[4], XC[4], s0[JT], s1[JT];
             right_shifted(C, orrC); right_shifted(D, orrD);
             pair_sums(C, orrC, B.todd, XU);
             pair_sums(D, orrD, B.todd, XC);
-            thumb_pairs_begin<JT>(B, T, XU, XC, s0, s1);
+            if constexpr (TM >= 4) thumb_pairs_static<JT, TM>(XU, XC, s0, s1);
+            else thumb_pairs_begin<JT>(B, T, XU, XC, s0, s1);
             thumb_pairs_end<JT>(T, infoD, s0, s1);
         }
 #endif
@@ -576,18 +592,18 @@ __global__ void __launch_bounds__(MAXT, MINB) k1_fused_kernel(K1Params P)
     while (true) {
         const int ng = grp + 1 == NGRP ? 0 : grp + 1;
         const uint32_t np = grp + 1 == NGRP ? par ^ 1u : par;
-        uint32_t tk = load_row<2, JT, PAIR>(B, q, grp, par, ok, full_bar(3 * ng), np, tid, first, last, R2, T);
-        lap_step<JT, PAIR>(B, R0, R1, R2, A, T, row_info(q - 1));
+        uint32_t tk = load_row<2, JT, TM>(B, q, grp, par, ok, full_bar(3 * ng), np, tid, first, last, R2, T);
+        lap_step<JT, TM>(B, R0, R1, R2, A, T, row_info(q - 1));
         release_finish<2>(B, q, grp, tk);
         if (q == nseq - 1) { band_end(R1, R2); break; }
         q++; grp = ng; par = np;
-        tk = load_row<0, JT, PAIR>(B, q, grp, par, ok, full_bar(3 * grp + 1), par, tid, first, last, R0, T);
-        lap_step<JT, PAIR>(B, R1, R2, R0, A, T, row_info(q - 1));
+        tk = load_row<0, JT, TM>(B, q, grp, par, ok, full_bar(3 * grp + 1), par, tid, first, last, R0, T);
+        lap_step<JT, TM>(B, R1, R2, R0, A, T, row_info(q - 1));
         release_finish<0>(B, q, grp, tk);
         if (q == nseq - 1) { band_end(R2, R0); break; }
         q++;
-        tk = load_row<1, JT, PAIR>(B, q, grp, par, ok, full_bar(3 * grp + 2), par, tid, first, last, R1, T);
-        lap_step<JT, PAIR>(B, R2, R0, R1, A, T, row_info(q - 1));
+        tk = load_row<1, JT, TM>(B, q, grp, par, ok, full_bar(3 * grp + 2), par, tid, first, last, R1, T);
+        lap_step<JT, TM>(B, R2, R0, R1, A, T, row_info(q - 1));
         release_finish<1>(B, q, grp, tk);
         if (q == nseq - 1) { band_end(R0, R1); break; }
         q++;
@@ -624,7 +640,7 @@ __global__ void __launch_bounds__(MAXT, MINB) k1_fused_kernel(K1Params P)
     if (!is_last) return;
 
     // ---- this warp is the last one of the band: the staged thumbnail rows (contiguous in the thumbnail) go out ----
-    if (PAIR) {
+    if ((TM != 0)) {
         const int ty0 = tab->thumb_row_begin[b], nty = tab->thumb_row_begin[b + 1] - ty0;
         const uint4 *src = (const uint4 *)(smem + HDR + NRS * P.row_bytes + 64 + SLOT * nthr + 64);
         uint4 *dst = (uint4 *)(P.thumbs + ((size_t)f * AVD_T + ty0) * AVD_T);
@@ -679,12 +695,12 @@ bool k1_fused_supported(int H, int W, size_t pitch, size_t fstride, const void *
     return true;
 }
 
-template <int MAXT, int MINB, int JT, bool PAIR>
+template <int MAXT, int MINB, int JT, int TM>
 static int k1_launch(avd_ctx *ctx, const K1Params &P, int n, size_t smem, int threads, cudaStream_t st)
 {
     static size_t smem_set = 0;
     if (smem > smem_set) {
-        AVD_CUDA(ctx, cudaFuncSetAttribute(k1_fused_kernel<MAXT, MINB, JT, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        AVD_CUDA(ctx, cudaFuncSetAttribute(k1_fused_kernel<MAXT, MINB, JT, TM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         smem_set = smem;
     }
     for (int f0 = 0; f0 < n; f0 += 65535) {                          // grid.y limit
@@ -693,7 +709,12 @@ static int k1_launch(avd_ctx *ctx, const K1Params &P, int n, size_t smem, int th
         Q.bgr = P.bgr + (size_t)f0 * P.fstride; Q.rec = P.rec + f0;
         Q.thumbs = P.thumbs + (size_t)f0 * AVD_T * AVD_T; Q.area32 = P.area32 + (size_t)f0 * 1024;
         Q.frame0 = f0;
-        AVD_LAUNCH(ctx, "k1_fused", st, (k1_fused_kernel<MAXT, MINB, JT, PAIR><<<dim3(AVD_D, nb), threads, smem, st>>>(Q)));
+        if (getenv("AVD_DEBUG")) {
+            cudaFuncAttributes fa; cudaFuncGetAttributes(&fa, k1_fused_kernel<MAXT, MINB, JT, TM>);
+            fprintf(stderr, "k1_launch<%d,%d,%d,%d>: threads %d smem %zu | maxThreads %d regs %d maxDyn %d static %zu smem_set %zu\n", MAXT, MINB, JT, TM, threads, smem,
+                    fa.maxThreadsPerBlock, fa.numRegs, fa.maxDynamicSharedSizeBytes, fa.sharedSizeBytes, smem_set);
+        }
+        AVD_LAUNCH(ctx, "k1_fused", st, (k1_fused_kernel<MAXT, MINB, JT, TM><<<dim3(AVD_D, nb), threads, smem, st>>>(Q)));
     }
     return AVD_OK;
 }
@@ -715,16 +736,18 @@ int k1_fused(avd_ctx *ctx, const uint8_t *d_bgr, int n, int H, int W, size_t pit
             htab->ly[i].a0 + htab->ly[i].a1 != 2048) pair = false;
     if (threads <= 128) {                                            // <= 2048 px wide
         if (pair) {
-            if (jt <= 3) return k1_launch<128, K1_MINB, 3, true>(ctx, P, n, smem, threads, st);
-            return k1_launch<128, K1_MINB, 4, true>(ctx, P, n, smem, threads, st);
+            if (W == 1280) return k1_launch<128, K1_MINB, 4, 4>(ctx, P, n, smem, threads, st);
+            if (jt <= 3) return k1_launch<128, K1_MINB, 3, 1>(ctx, P, n, smem, threads, st);
+            return k1_launch<128, K1_MINB, 4, 1>(ctx, P, n, smem, threads, st);
         }
-        if (jt <= 3) return k1_launch<128, K1_MINB, 3, false>(ctx, P, n, smem, threads, st);
-        return k1_launch<128, K1_MINB, 4, false>(ctx, P, n, smem, threads, st);
+        if (jt <= 3) return k1_launch<128, K1_MINB, 3, 0>(ctx, P, n, smem, threads, st);
+        return k1_launch<128, K1_MINB, 4, 0>(ctx, P, n, smem, threads, st);
     }
     if (pair) {
-        if (jt <= 2) return k1_launch<256, 2, 2, true>(ctx, P, n, smem, threads, st);
-        return k1_launch<256, 2, 3, true>(ctx, P, n, smem, threads, st);
+        if (W == 2560) return k1_launch<256, 2, 2, 8>(ctx, P, n, smem, threads, st);
+        if (jt <= 2) return k1_launch<256, 2, 2, 1>(ctx, P, n, smem, threads, st);
+        return k1_launch<256, 2, 3, 1>(ctx, P, n, smem, threads, st);
     }
-    if (jt <= 2) return k1_launch<256, 2, 2, false>(ctx, P, n, smem, threads, st);
-    return k1_launch<256, 2, 3, false>(ctx, P, n, smem, threads, st);
+    if (jt <= 2) return k1_launch<256, 2, 2, 0>(ctx, P, n, smem, threads, st);
+    return k1_launch<256, 2, 3, 0>(ctx, P, n, smem, threads, st);
 }
