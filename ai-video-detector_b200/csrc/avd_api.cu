@@ -294,7 +294,8 @@ int avd_frames_features(avd_ctx *ctx, const uint8_t *d_bgr, int n, int H, int W,
         d_area32 = ctx->area32;
     }
     K1FixArgs fix{d_bgr, row_pitch, frame_stride, tab, nullptr};
-    const bool streaming = ctx->k1_mode == 0 && k1_fused_supported(H, W, row_pitch, frame_stride, d_bgr, htab);
+    // the streaming kernel writes the thumbnail rows with 128-bit stores
+    const bool streaming = ctx->k1_mode == 0 && ((uintptr_t)d_thumbs % 16) == 0 && k1_fused_supported(H, W, row_pitch, frame_stride, d_bgr, htab);
     if (streaming) {
         if ((rc = avd_ensure(ctx, (void **)&ctx->fixlist, &ctx->fixlist_cap, ((size_t)n * 1024 + 1) * sizeof(uint32_t)))) return rc;
         fix.list = ctx->fixlist;
