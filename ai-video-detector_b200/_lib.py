@@ -19,7 +19,7 @@ REC_HAS_PREV, REC_HAS_FLOW = 1, 2
 SYMBOLS = ["avd_version", "avd_device_count", "avd_create", "avd_destroy", "avd_last_error", "avd_sync",
            "avd_host_alloc", "avd_host_free", "avd_frames_features", "avd_flow_stats", "avd_flow_fields",
            "avd_gray", "avd_analyze_host", "avd_launch_count", "avd_set_k1_mode", "avd_profile_enable",
-           "avd_profile_read"]
+           "avd_profile_read", "avd_shape_plan"]
 
 
 class AvdError(RuntimeError):

@@ -60,6 +60,48 @@ static void build_lin_taps(int ssize, int dsize, LinTap *taps, bool is_y)
     }
 }
 
+// Everything the kernels need to know about a frame shape; pure host code (also exported for the CPU tests).
+static void build_shape_tables(int H, int W, ShapeTables &t)
+{
+    build_area_cells(W, AVD_D, t.ax);
+    build_area_cells(H, AVD_D, t.ay);
+    build_lin_taps(W, AVD_T, t.lx, false);
+    build_lin_taps(H, AVD_T, t.ly, true);
+    double sx = (double)W / AVD_D, sy = (double)H / AVD_D;
+    t.isx = (int)sx; t.isy = (int)sy;
+    t.area_int = fabs(sx - t.isx) < 2.220446049250313e-16 && fabs(sy - t.isy) < 2.220446049250313e-16;
+    t.inv_area = 1.f / (float)(t.isx * t.isy);
+    t.thumb_2x2 = (W == 2 * AVD_T && H == 2 * AVD_T);
+    // band b of the fused kernels owns source rows [ceil(b*H/32), ceil((b+1)*H/32))
+    for (int b = 0; b <= AVD_D; b++) t.row_owner_begin[b] = b == AVD_D ? H : (int)ceil(b * sy);
+    // thumbnail row ty belongs to the band that owns its top tap row
+    int ty = 0;
+    for (int b = 0; b < AVD_D; b++) {
+        t.thumb_row_begin[b] = ty;
+        while (ty < AVD_T && (t.thumb_2x2 ? 2 * ty : t.ly[ty].i0) < t.row_owner_begin[b + 1]) ty++;
+    }
+    t.thumb_row_begin[AVD_D] = AVD_T;
+    // thumbnail columns per 16-pixel strip (streaming kernel)
+    t.strip_ntx_max = 0;
+    for (int s = 0, tx = 0; s < 256; s++) {
+        while (tx < AVD_T && t.lx[tx].i0 < 16 * s) tx++;
+        int cnt = 0;
+        while (tx + cnt < AVD_T && t.lx[tx + cnt].i0 < 16 * s + 16) cnt++;
+        t.strip_tx0[s] = (uint16_t)tx; t.strip_ntx[s] = (uint8_t)(cnt > 255 ? 255 : cnt);
+        if (16 * s < W && cnt > t.strip_ntx_max) t.strip_ntx_max = cnt;
+    }
+    if (H <= 4096) {
+        bool single_role = true;
+        for (int y = 0; y < AVD_T && single_role; y++) {
+            const LinTap &v = t.ly[y];
+            if (v.i1 != v.i0 + 1 || t.rowinfo[v.i0] || t.rowinfo[v.i1]) { single_role = false; break; }
+            t.rowinfo[v.i0] = 1u | ((uint32_t)v.a0 << 2) | ((uint32_t)y << 16);
+            t.rowinfo[v.i1] = 3u | ((uint32_t)v.a1 << 2) | ((uint32_t)y << 16);
+        }
+        if (!single_role) memset(t.rowinfo, 0, sizeof t.rowinfo);
+    }
+}
+
 int avd_get_tables(avd_ctx *ctx, int H, int W, const ShapeTables **dev, const ShapeTables **host)
 {
     auto key = std::make_pair(H, W);
@@ -67,43 +109,7 @@ int avd_get_tables(avd_ctx *ctx, int H, int W, const ShapeTables **dev, const Sh
     if (it == ctx->tables.end()) {
         std::unique_ptr<ShapeTables> tp(new ShapeTables());   // 21 KB, value-initialised: keep it off the stack
         ShapeTables &t = *tp;
-        build_area_cells(W, AVD_D, t.ax);
-        build_area_cells(H, AVD_D, t.ay);
-        build_lin_taps(W, AVD_T, t.lx, false);
-        build_lin_taps(H, AVD_T, t.ly, true);
-        double sx = (double)W / AVD_D, sy = (double)H / AVD_D;
-        t.isx = (int)sx; t.isy = (int)sy;
-        t.area_int = fabs(sx - t.isx) < 2.220446049250313e-16 && fabs(sy - t.isy) < 2.220446049250313e-16;
-        t.inv_area = 1.f / (float)(t.isx * t.isy);
-        t.thumb_2x2 = (W == 2 * AVD_T && H == 2 * AVD_T);
-        // band b of the fused kernel owns source rows [ceil(b*H/32), ceil((b+1)*H/32))
-        for (int b = 0; b <= AVD_D; b++) t.row_owner_begin[b] = b == AVD_D ? H : (int)ceil(b * sy);
-        // thumbnail row ty belongs to the band that owns its top tap row
-        int ty = 0;
-        for (int b = 0; b < AVD_D; b++) {
-            t.thumb_row_begin[b] = ty;
-            while (ty < AVD_T && (t.thumb_2x2 ? 2 * ty : t.ly[ty].i0) < t.row_owner_begin[b + 1]) ty++;
-        }
-        t.thumb_row_begin[AVD_D] = AVD_T;
-        // thumbnail columns per 16-pixel strip (streaming kernel)
-        t.strip_ntx_max = 0;
-        for (int s = 0, tx = 0; s < 256; s++) {
-            while (tx < AVD_T && t.lx[tx].i0 < 16 * s) tx++;
-            int cnt = 0;
-            while (tx + cnt < AVD_T && t.lx[tx + cnt].i0 < 16 * s + 16) cnt++;
-            t.strip_tx0[s] = (uint16_t)tx; t.strip_ntx[s] = (uint8_t)(cnt > 255 ? 255 : cnt);
-            if (16 * s < W && cnt > t.strip_ntx_max) t.strip_ntx_max = cnt;
-        }
-        if (H <= 4096) {
-            bool single_role = true;
-            for (int y = 0; y < AVD_T && single_role; y++) {
-                const LinTap &v = t.ly[y];
-                if (v.i1 != v.i0 + 1 || t.rowinfo[v.i0] || t.rowinfo[v.i1]) { single_role = false; break; }
-                t.rowinfo[v.i0] = 1u | ((uint32_t)v.a0 << 2) | ((uint32_t)y << 16);
-                t.rowinfo[v.i1] = 3u | ((uint32_t)v.a1 << 2) | ((uint32_t)y << 16);
-            }
-            if (!single_role) memset(t.rowinfo, 0, sizeof t.rowinfo);
-        }
+        build_shape_tables(H, W, t);
         ShapeTables *d = nullptr;
         AVD_CUDA(ctx, cudaMalloc(&d, sizeof(ShapeTables)));
         AVD_CUDA(ctx, cudaMemcpy(d, &t, sizeof(ShapeTables), cudaMemcpyHostToDevice));
@@ -257,6 +263,28 @@ int avd_profile_read(avd_ctx *ctx, char *buf, size_t cap)
     js += "}";
     if (js.size() + 1 > cap) { ctx->err = "profile buffer too small"; return AVD_ERR_ARG; }
     memcpy(buf, js.c_str(), js.size() + 1);
+    return AVD_OK;
+}
+
+// Host-only (no device, no context): the per-shape plan of the frame kernels, for tests and integration debugging.
+int avd_shape_plan(int H, int W, avd_shape_plan_t *out)
+{
+    if (!out || H < AVD_D || W < AVD_D) return AVD_ERR_ARG;
+    std::unique_ptr<ShapeTables> tp(new ShapeTables());
+    ShapeTables &t = *tp;
+    build_shape_tables(H, W, t);
+    memset(out, 0, sizeof *out);
+    out->area_int = t.area_int; out->thumb_2x2 = t.thumb_2x2; out->strip_ntx_max = t.strip_ntx_max;
+    for (int b = 0; b <= AVD_D; b++) { out->row_owner_begin[b] = t.row_owner_begin[b]; out->thumb_row_begin[b] = t.thumb_row_begin[b]; }
+    for (int i = 0; i < AVD_T; i++) {
+        out->lx_i0[i] = t.lx[i].i0; out->lx_a0[i] = t.lx[i].a0; out->lx_a1[i] = t.lx[i].a1;
+        out->ly_i0[i] = t.ly[i].i0; out->ly_a0[i] = t.ly[i].a0; out->ly_a1[i] = t.ly[i].a1;
+    }
+    for (int s = 0; s < 256; s++) { out->strip_tx0[s] = t.strip_tx0[s]; out->strip_ntx[s] = t.strip_ntx[s]; }
+    for (int r = 0; r < H && r < 4096; r++) out->rowinfo[r] = t.rowinfo[r];
+    // which per-frame kernel a dense, 16-byte aligned buffer of this shape gets (0 streaming, 2 banded, 1 generic)
+    const size_t pitch = (size_t)W * 3;
+    out->k1_path = k1_fused_supported(H, W, pitch, pitch * H, nullptr, &t) ? 0 : (k1_banded_supported(H, W, pitch, pitch * H, nullptr) ? 2 : 1);
     return AVD_OK;
 }
 

@@ -124,6 +124,22 @@ int avd_profile_read(avd_ctx *ctx, char *buf, size_t cap);
  * multi-kernel path, 2 = skip the streaming kernel (banded or generic).  For tests. */
 int avd_set_k1_mode(avd_ctx *ctx, int mode);
 
+/*
+ * Host-only view of the per-shape plan the frame kernels run from (no device needed): band ownership of source
+ * rows, INTER_LINEAR taps (video.py:43), thumbnail columns per 16-pixel strip, thumbnail role of every source row
+ * (bit0 tap row, bit1 bottom tap, bits 2-13 vertical weight, bits 16-24 thumbnail row) and the kernel a dense
+ * aligned buffer of this shape is given (0 streaming fused, 2 banded fused, 1 generic).  For tests and debugging.
+ */
+typedef struct avd_shape_plan_t {
+    int area_int, thumb_2x2, strip_ntx_max, k1_path;
+    int row_owner_begin[AVD_HASH_SIDE + 1], thumb_row_begin[AVD_HASH_SIDE + 1];
+    int lx_i0[AVD_THUMB], lx_a0[AVD_THUMB], lx_a1[AVD_THUMB];
+    int ly_i0[AVD_THUMB], ly_a0[AVD_THUMB], ly_a1[AVD_THUMB];
+    int strip_tx0[256], strip_ntx[256];
+    uint32_t rowinfo[4096];
+} avd_shape_plan_t;
+int avd_shape_plan(int H, int W, avd_shape_plan_t *out);
+
 #ifdef __cplusplus
 }
 #endif

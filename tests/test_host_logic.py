@@ -180,3 +180,92 @@ def test_frame_chunk_sharding_world2_gloo(tmp_path):
     outs = [p.communicate(timeout=240)[0] for p in procs]
     assert all(p.returncode == 0 for p in procs), outs
     assert "SHARD_OK" in outs[0]
+
+
+# ---- per-shape plan of the frame kernels (host code of libavd.so, no device needed) --------------------------------
+class _Plan(C.Structure):
+    _fields_ = [("area_int", C.c_int), ("thumb_2x2", C.c_int), ("strip_ntx_max", C.c_int), ("k1_path", C.c_int),
+                ("row_owner_begin", C.c_int * 33), ("thumb_row_begin", C.c_int * 33),
+                ("lx_i0", C.c_int * 320), ("lx_a0", C.c_int * 320), ("lx_a1", C.c_int * 320),
+                ("ly_i0", C.c_int * 320), ("ly_a0", C.c_int * 320), ("ly_a1", C.c_int * 320),
+                ("strip_tx0", C.c_int * 256), ("strip_ntx", C.c_int * 256), ("rowinfo", C.c_uint32 * 4096)]
+
+
+def _plan(H, W):
+    from avd_b200 import _lib
+    if not os.path.exists(_lib.LIB_PATH):
+        import __graft_entry__ as g
+        g.build()
+    L = C.CDLL(_lib.LIB_PATH)
+    L.avd_shape_plan.argtypes = [C.c_int, C.c_int, C.POINTER(_Plan)]
+    p = _Plan()
+    assert L.avd_shape_plan(H, W, C.byref(p)) == 0
+    return p
+
+
+def _lin_taps(ssize, dsize=320):
+    """INTER_LINEAR 8-bit taps as the library builds them (float32 arithmetic), x-axis form."""
+    scale = 1.0 / (dsize / ssize)
+    out = []
+    for d in range(dsize):
+        f = np.float32((d + 0.5) * scale - 0.5)
+        s = int(np.floor(f))
+        f = np.float32(f - np.float32(s))
+        if s < 0:
+            f, s = np.float32(0), 0
+        if s >= ssize - 1:
+            f, s = np.float32(0), ssize - 1
+        out.append((s, int(np.rint(np.float32(np.float32(1) - f) * np.float32(2048))), int(np.rint(f * np.float32(2048)))))
+    return out
+
+
+@pytest.mark.parametrize("shape", [(720, 1280), (1080, 1920), (1440, 2560), (2160, 3840), (480, 854), (480, 640), (648, 1344)])
+def test_shape_plan_taps_bands_and_strips(shape):
+    H, W = shape
+    p = _plan(H, W)
+    assert [(p.lx_i0[i], p.lx_a0[i], p.lx_a1[i]) for i in range(320)] == _lin_taps(W)
+    ly = _lin_taps(H)
+    assert [(p.ly_i0[i], p.ly_a0[i], p.ly_a1[i]) for i in range(320)] == ly      # downscaling: no row clipping in play
+    # bands: every source row has exactly one owner, band b starts at ceil(b*H/32)
+    own = list(p.row_owner_begin)
+    assert own[0] == 0 and own[32] == H and all(own[b] == -(-b * H // 32) for b in range(32)) and own == sorted(own)
+    # every thumbnail row belongs to the band that owns its top tap row
+    trb = list(p.thumb_row_begin)
+    assert trb[0] == 0 and trb[32] == 320
+    for b in range(32):
+        for ty in range(trb[b], trb[b + 1]):
+            assert own[b] <= p.ly_i0[ty] < own[b + 1]
+    # every thumbnail column belongs to exactly one 16-pixel strip: the one that holds its left tap
+    seen = []
+    for s in range((W + 15) // 16):
+        for k in range(p.strip_ntx[s]):
+            tx = p.strip_tx0[s] + k
+            assert 16 * s <= p.lx_i0[tx] < 16 * s + 16
+            seen.append(tx)
+    assert seen == list(range(320))
+    assert p.strip_ntx_max == max(p.strip_ntx[s] for s in range((W + 15) // 16))
+
+
+@pytest.mark.parametrize("shape", [(720, 1280), (1080, 1920), (2160, 3840), (648, 1344)])
+def test_shape_plan_row_roles(shape):
+    """Thumbnail role of every source row (streaming kernel): top / bottom tap of exactly one thumbnail row."""
+    H, W = shape
+    p = _plan(H, W)
+    want = [0] * H
+    for ty in range(320):
+        y0 = p.ly_i0[ty]
+        want[y0] = 1 | (p.ly_a0[ty] << 2) | (ty << 16)
+        want[y0 + 1] = 3 | (p.ly_a1[ty] << 2) | (ty << 16)
+        assert p.ly_a0[ty] + p.ly_a1[ty] == 2048
+    assert list(p.rowinfo[:H]) == want
+
+
+def test_shape_plan_kernel_choice():
+    """Which per-frame kernel a dense aligned buffer gets: 0 streaming fused, 2 banded fused, 1 generic."""
+    want = {(1080, 1920): 0, (720, 1280): 0, (1440, 2560): 0, (2160, 3840): 0, (648, 1344): 0, (960, 1280): 0,
+            (480, 640): 2, (640, 640): 2, (360, 640): 2, (1080, 1936): 2,   # W % 16 == 0 only
+            (480, 854): 1, (333, 777): 1, (32, 32): 2,
+            (600, 1920): 2}                                                   # H < 640: a tap row would have two roles
+    for (H, W), k in want.items():
+        assert _plan(H, W).k1_path == k, (H, W)
+    assert _plan(960, 1280).area_int == 1 and _plan(1080, 1920).area_int == 0 and _plan(640, 640).thumb_2x2 == 1
