@@ -492,7 +492,8 @@ int k1_banded(avd_ctx *ctx, const uint8_t *d_bgr, int n, int H, int W, size_t pi
     if (smem > 227 * 1024) { ctx->err = "fused K1: frame too wide for shared memory"; return AVD_ERR_ARG; }
     int threads = ((W / 16) + 31) / 32 * 32;
     const bool narrow = threads <= 128;                              // <= 2048 px wide: 5 CTAs / SM, <= 102 registers
-    static size_t smem_set[2] = {0, 0};
+    static size_t smem_set_dev[64][2] = {};          // per device: function attributes belong to the device's context
+    size_t *smem_set = smem_set_dev[ctx->device & 63];
     if (smem > smem_set[narrow]) {
         if (narrow) AVD_CUDA(ctx, cudaFuncSetAttribute(k1_banded_kernel<128, K1_MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         else AVD_CUDA(ctx, cudaFuncSetAttribute(k1_banded_kernel<256, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -698,10 +698,11 @@ bool k1_fused_supported(int H, int W, size_t pitch, size_t fstride, const void *
 template <int MAXT, int MINB, int JT, int TM>
 static int k1_launch(avd_ctx *ctx, const K1Params &P, int n, size_t smem, int threads, cudaStream_t st)
 {
-    static size_t smem_set = 0;
-    if (smem > smem_set) {
+    static size_t smem_set[64] = {};                 // per device: function attributes belong to the device's context
+    size_t &set = smem_set[ctx->device & 63];
+    if (smem > set) {
         AVD_CUDA(ctx, cudaFuncSetAttribute(k1_fused_kernel<MAXT, MINB, JT, TM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        smem_set = smem;
+        set = smem;
     }
     for (int f0 = 0; f0 < n; f0 += 65535) {                          // grid.y limit
         int nb = n - f0 < 65535 ? n - f0 : 65535;
@@ -711,8 +712,8 @@ static int k1_launch(avd_ctx *ctx, const K1Params &P, int n, size_t smem, int th
         Q.frame0 = f0;
         if (getenv("AVD_DEBUG")) {
             cudaFuncAttributes fa; cudaFuncGetAttributes(&fa, k1_fused_kernel<MAXT, MINB, JT, TM>);
-            fprintf(stderr, "k1_launch<%d,%d,%d,%d>: threads %d smem %zu | maxThreads %d regs %d maxDyn %d static %zu smem_set %zu\n", MAXT, MINB, JT, TM, threads, smem,
-                    fa.maxThreadsPerBlock, fa.numRegs, fa.maxDynamicSharedSizeBytes, fa.sharedSizeBytes, smem_set);
+            fprintf(stderr, "k1_launch<%d,%d,%d,%d>: threads %d smem %zu | maxThreads %d regs %d maxDyn %d static %zu\n", MAXT, MINB, JT, TM, threads, smem,
+                    fa.maxThreadsPerBlock, fa.numRegs, fa.maxDynamicSharedSizeBytes, fa.sharedSizeBytes);
         }
         AVD_LAUNCH(ctx, "k1_fused", st, (k1_fused_kernel<MAXT, MINB, JT, TM><<<dim3(AVD_D, nb), threads, smem, st>>>(Q)));
     }

@@ -1,6 +1,6 @@
 #!/bin/bash
-# time every built variant's K2 on the same input (no sub-batching unless env says so): scripts/ab_k2.sh n reps
+# time every built K2 variant: scripts/ab_k2.sh n reps [name-filter]
 cd "$(dirname "$0")/.."
-for so in ai-video-detector_b200/csrc/variants/libavd_*.so; do
+for so in ai-video-detector_b200/csrc/variants/libavd_${3:-}*.so; do
   echo -n "$(basename $so): "; AVD_LIB=$PWD/$so python scripts/prof_k2.py $1 $2 | tail -1
 done

@@ -77,8 +77,10 @@ def test_frame_features_vs_reference_golden(golden, golden_arrays, synth, torch,
 
 def test_fused_equals_generic_on_batches(synth, torch, eng):
     """The three K1 implementations must agree byte for byte on a batch (incl. Hamming chain)."""
+    # streaming kernel: pair-sum thumbnail (1280/1920/2560/3840 wide; static lanes at 1280 and 2560) and general two-tap
+    # thumbnail (1344, 2048, 4096 wide), integer and fractional INTER_AREA rows; banded kernel: 128..704 wide; generic: rest
     for (H, W) in [(720, 1280), (1080, 1920), (96, 128), (270, 480), (360, 640), (960, 1280), (1440, 2560), (2160, 3840),
-                   (648, 704), (1000, 4096)]:
+                   (648, 704), (1000, 4096), (648, 1344), (800, 2048), (4096, 1280), (641, 3200)]:
         clip = synth.Clip(40, H, W, seed=5, events=True)
         fr = torch.from_numpy(np.stack([clip[i] for i in (0, 3, 12, 13, 20, 25, 31, 39)])).cuda()
         outs = []
@@ -114,6 +116,22 @@ def test_area_rounding_boundaries(torch, eng, oracle):
         assert np.array_equal(eng.gray(d[i]).cpu().numpy(), x)
         assert np.array_equal(outs[0][1][i], oracle.area32(x)), i
     assert outs[0][0] == outs[1][0] and np.array_equal(outs[0][1], outs[1][1])
+
+
+def test_streaming_kernel_padded_pitch(synth, torch, eng):
+    """Row pitch > 3W (16-byte aligned) and a frame stride > H*pitch through the streaming kernel."""
+    H, W = 720, 1280
+    f = synth.noise_frames(3, H, W, 13)
+    big = torch.zeros((3, H + 2, W * 3 + 64), dtype=torch.uint8, device="cuda")
+    big[:, :H, :W * 3] = torch.from_numpy(f.reshape(3, H, W * 3)).cuda()
+    view = big[:, :H, :W * 3].unflatten(2, (W, 3))
+    outs = []
+    for mode in (0, 1):
+        eng.set_k1_mode(mode)
+        rec, th, ar = eng.frames_features(view, want_area32=True)
+        outs.append((rec.cpu().numpy().tobytes(), th.cpu().numpy().tobytes(), ar.cpu().numpy().tobytes()))
+    eng.set_k1_mode(0)
+    assert outs[0] == outs[1]
 
 
 def test_padded_pitch_and_unaligned_views(synth, torch, eng, oracle):
