@@ -110,56 +110,73 @@ __global__ void __launch_bounds__(128) pyr_kernel(ImgSrc src, float *__restrict_
 }
 
 // ---- polynomial expansion ----------------------------------------------------------------------------
-// R[img][c][y][x], c = 0..4, planar.  Vertical pass float32 -> shared, horizontal pass float64 accumulators.
-constexpr int PE_TW = 32, PE_TH = 8, PE_HALO = 5;
+// R[img][c][y][x], c = 0..4, planar.  Vertical pass in float32, horizontal pass with float64 accumulators, in the
+// library's operation order.  A CTA owns PE_ROWS full-width rows of one image; a thread owns a column:
+// it reads its 18 input values once (coalesced across the CTA), produces the three vertical moments of its 8 rows
+// out of registers, parks them in shared memory (with the replicated border columns) and then runs the horizontal
+// pass of its 8 pixels out of shared memory.
+constexpr int PE_ROWS = 8, PE_HALO = 5;
 
-__global__ void __launch_bounds__(PE_TW *PE_TH) polyexp_kernel(const float *__restrict__ pyr, float *__restrict__ Rall, int k)
+__global__ void __launch_bounds__(T) polyexp_kernel(const float *__restrict__ pyr, float *__restrict__ Rall, int k)
 {
-    const int s = lvl_size(k);
-    const float *I = pyr + (size_t)blockIdx.z * PYR_PX + lvl_off(k);
-    float *R = Rall + (size_t)blockIdx.z * PYR_PX * 5 + (size_t)lvl_off(k) * 5;
-    __shared__ float v[3][PE_TH][PE_TW + 2 * PE_HALO];
-    int x0 = blockIdx.x * PE_TW, y0 = blockIdx.y * PE_TH;
-    int tid = threadIdx.y * PE_TW + threadIdx.x;
-    for (int idx = tid; idx < PE_TH * (PE_TW + 2 * PE_HALO); idx += PE_TW * PE_TH) {
-        int ty = idx / (PE_TW + 2 * PE_HALO), tc = idx % (PE_TW + 2 * PE_HALO);
-        int gx = clampi(x0 + tc - PE_HALO, 0, s - 1), gy = min(y0 + ty, s - 1);
-        float c0 = I[(size_t)gy * s + gx];
-        float r0 = c0 * FC.g[0], r1 = 0.f, r2 = 0.f;
+    extern __shared__ float pe_v[];                                    // [3][PE_ROWS][s + 2*PE_HALO]
+    const int s = lvl_size(k), vw = s + 2 * PE_HALO;
+    const float *I = pyr + (size_t)blockIdx.y * PYR_PX + lvl_off(k);
+    float *R = Rall + (size_t)blockIdx.y * PYR_PX * 5 + (size_t)lvl_off(k) * 5;
+    const int x = threadIdx.x, y0 = blockIdx.x * PE_ROWS;
+    if (x < s) {
+        float w[PE_ROWS + 2 * PE_HALO];
 #pragma unroll
-        for (int j = 1; j <= 5; j++) {
-            float a = I[(size_t)max(gy - j, 0) * s + gx], b = I[(size_t)min(gy + j, s - 1) * s + gx];
-            float p = a + b;
-            r0 = r0 + FC.g[j] * p;
-            r1 = r1 + FC.xg[j] * (b - a);
-            r2 = r2 + FC.xxg[j] * p;
+        for (int i = 0; i < PE_ROWS + 2 * PE_HALO; i++) w[i] = I[(size_t)clampi(y0 - PE_HALO + i, 0, s - 1) * s + x];
+#pragma unroll
+        for (int r = 0; r < PE_ROWS; r++) {
+            const float c0 = w[r + PE_HALO];
+            float r0 = c0 * FC.g[0], r1 = 0.f, r2 = 0.f;
+#pragma unroll
+            for (int j = 1; j <= 5; j++) {
+                const float a = w[r + PE_HALO - j], b = w[r + PE_HALO + j];
+                const float p = a + b;
+                r0 = r0 + FC.g[j] * p;
+                r1 = r1 + FC.xg[j] * (b - a);
+                r2 = r2 + FC.xxg[j] * p;
+            }
+            float *v0 = pe_v + (size_t)r * vw + x + PE_HALO, *v1 = v0 + (size_t)PE_ROWS * vw, *v2 = v1 + (size_t)PE_ROWS * vw;
+            *v0 = r0; *v1 = r1; *v2 = r2;
+            if (x == 0) {
+#pragma unroll
+                for (int h = 1; h <= PE_HALO; h++) { v0[-h] = r0; v1[-h] = r1; v2[-h] = r2; }
+            }
+            if (x == s - 1) {
+#pragma unroll
+                for (int h = 1; h <= PE_HALO; h++) { v0[h] = r0; v1[h] = r1; v2[h] = r2; }
+            }
         }
-        v[0][ty][tc] = r0; v[1][ty][tc] = r1; v[2][ty][tc] = r2;
     }
     __syncthreads();
-    int x = x0 + threadIdx.x, y = y0 + threadIdx.y;
-    if (x >= s || y >= s) return;
-    const int c = threadIdx.x + PE_HALO, ty = threadIdx.y;
-    double b1 = (double)(v[0][ty][c] * FC.g[0]), b2 = 0, b3 = (double)(v[1][ty][c] * FC.g[0]), b4 = 0,
-           b5 = (double)(v[2][ty][c] * FC.g[0]), b6 = 0;
+    if (x >= s) return;
+    const size_t plane = (size_t)s * s;
+#pragma unroll 1
+    for (int r = 0; r < PE_ROWS; r++) {
+        const float *v0 = pe_v + (size_t)r * vw + x + PE_HALO, *v1 = v0 + (size_t)PE_ROWS * vw, *v2 = v1 + (size_t)PE_ROWS * vw;
+        double b1 = (double)(v0[0] * FC.g[0]), b2 = 0, b3 = (double)(v1[0] * FC.g[0]), b4 = 0, b5 = (double)(v2[0] * FC.g[0]), b6 = 0;
 #pragma unroll
-    for (int j = 1; j <= 5; j++) {
-        float p0 = v[0][ty][c + j], m0 = v[0][ty][c - j], p1 = v[1][ty][c + j], m1 = v[1][ty][c - j],
-              p2 = v[2][ty][c + j], m2 = v[2][ty][c - j];
-        double tg = (double)(p0 + m0);
-        b1 += tg * (double)FC.g[j];
-        b4 += tg * (double)FC.xxg[j];
-        b2 += (double)((p0 - m0) * FC.xg[j]);
-        b3 += (double)((p1 + m1) * FC.g[j]);
-        b6 += (double)((p1 - m1) * FC.xg[j]);
-        b5 += (double)((p2 + m2) * FC.g[j]);
+        for (int j = 1; j <= 5; j++) {
+            const float p0 = v0[j], m0 = v0[-j], p1 = v1[j], m1 = v1[-j], p2 = v2[j], m2 = v2[-j];
+            const double tg = (double)(p0 + m0);
+            b1 += tg * (double)FC.g[j];
+            b4 += tg * (double)FC.xxg[j];
+            b2 += (double)((p0 - m0) * FC.xg[j]);
+            b3 += (double)((p1 + m1) * FC.g[j]);
+            b6 += (double)((p1 - m1) * FC.xg[j]);
+            b5 += (double)((p2 + m2) * FC.g[j]);
+        }
+        const size_t o = (size_t)(y0 + r) * s + x;
+        R[o] = (float)(b3 * FC.ig11);
+        R[plane + o] = (float)(b2 * FC.ig11);
+        R[2 * plane + o] = (float)(b1 * FC.ig03 + b5 * FC.ig33);
+        R[3 * plane + o] = (float)(b1 * FC.ig03 + b4 * FC.ig33);
+        R[4 * plane + o] = (float)(b6 * FC.ig55);
     }
-    size_t plane = (size_t)s * s, o = (size_t)y * s + x;
-    R[o] = (float)(b3 * FC.ig11);
-    R[plane + o] = (float)(b2 * FC.ig11);
-    R[2 * plane + o] = (float)(b1 * FC.ig03 + b5 * FC.ig33);
-    R[3 * plane + o] = (float)(b1 * FC.ig03 + b4 * FC.ig33);
-    R[4 * plane + o] = (float)(b6 * FC.ig55);
 }
 
 // ---- update matrices ---------------------------------------------------------------------------------
@@ -498,7 +515,7 @@ int k2_flow(avd_ctx *ctx, const uint8_t *d_prev, const uint8_t *d_next, size_t p
         AVD_LAUNCH(ctx, "pyr", st, pyr_kernel<0><<<dim3((320 * 320 + 127) / 128, ni), 128, 0, st>>>(src, pyr));
         for (int k = 3; k >= 0; k--) {
             int s = lvl_size(k);
-            AVD_LAUNCH(ctx, "polyexp", st, polyexp_kernel<<<dim3((s + PE_TW - 1) / PE_TW, (s + PE_TH - 1) / PE_TH, ni), dim3(PE_TW, PE_TH), 0, st>>>(pyr, R, k));
+            AVD_LAUNCH(ctx, "polyexp", st, polyexp_kernel<<<dim3(s / PE_ROWS, ni), (s + 31) / 32 * 32, 3 * PE_ROWS * (s + 2 * PE_HALO) * sizeof(float), st>>>(pyr, R, k));
         }
         float *cur = flowA, *prev = flowB;
         // Optional L2-resident sub-batching of levels 0/1 (AVD_K2_SB0 / AVD_K2_SB1 = pairs per sub-batch, 0 = off).
