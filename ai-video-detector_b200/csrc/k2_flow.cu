@@ -55,57 +55,49 @@ __device__ __forceinline__ float blur_row(const uint8_t *__restrict__ row, int x
     return a;
 }
 
-template <int R, int NX, int NY>
-__device__ __forceinline__ void blur_taps(const uint8_t *__restrict__ img, int xc, int yc, const float *__restrict__ k, float out[NY][NX])
-{
-    // rows yc-R .. yc+NY-1+R, columns xc .. xc+NX-1
-    float t[NY + 2 * R][NX];
-#pragma unroll
-    for (int r = 0; r < NY + 2 * R; r++) {
-        const uint8_t *row = img + (size_t)r101(yc - R + r, T) * T;
-#pragma unroll
-        for (int c = 0; c < NX; c++) t[r][c] = blur_row<R>(row, xc + c, k);
-    }
-#pragma unroll
-    for (int oy = 0; oy < NY; oy++)
-#pragma unroll
-        for (int c = 0; c < NX; c++) {
-            float a = k[0] * t[oy + R][c];
-#pragma unroll
-            for (int j = 1; j <= R; j++) a = a + k[j] * (t[oy + R - j][c] + t[oy + R + j][c]);
-            out[oy][c] = a;
-        }
-}
-
+// A CTA owns PYR_CW output columns of one image over the full height.  Phase A: the row-blurred values of the source
+// columns those outputs read, for all 320 source rows, go to shared memory once (the previous version recomputed them for
+// every output: 2-3x the work).  Phase B: column blur at the taps of each output and the resize arithmetic.
+constexpr int PYR_CW = 8;
 template <int K>
-__global__ void __launch_bounds__(128) pyr_kernel(ImgSrc src, float *__restrict__ pyr)
+__global__ void __launch_bounds__(256) pyr_kernel(ImgSrc src, float *__restrict__ pyr)
 {
-    constexpr int S = lvl_size(K);
-    int p = blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= S * S) return;
-    int img_i = blockIdx.y;
+    constexpr int S = lvl_size(K), ST = 1 << K, R = K == 0 ? 1 : (K == 1 ? 1 : (K == 2 ? 4 : 9)), N = K == 0 ? 1 : 2;
+    constexpr int OFF = K == 2 ? 1 : (K == 3 ? 3 : 0), NC = PYR_CW * N;
+    __shared__ float t[T][NC];
+    const int img_i = blockIdx.y, xo0 = blockIdx.x * PYR_CW;
     const uint8_t *img = img_ptr(src, img_i);
     float *out = pyr + (size_t)img_i * PYR_PX + lvl_off(K);
-    const int y = p / S, x = p % S;
-    if (K == 0) {
-        const float k0[2] = {0.5f, 0.25f};
-        float o[1][1];
-        blur_taps<1, 1, 1>(img, x, y, k0, o);
-        out[p] = o[0][0];
-    } else if (K == 1) {                   // 320 -> 160: exact 2x => 2x2 area mean
-        float o[2][2];
-        blur_taps<1, 2, 2>(img, 2 * x, 2 * y, FC.k1, o);
-        out[p] = (((o[0][0] + o[0][1]) + o[1][0]) + o[1][1]) * 0.25f;
-    } else if (K == 2) {                   // 320 -> 80: bilinear at 4x+1.5 (weights .5/.5)
-        float o[2][2];
-        blur_taps<4, 2, 2>(img, 4 * x + 1, 4 * y + 1, FC.k2, o);
-        float r0 = o[0][0] * 0.5f + o[0][1] * 0.5f, r1 = o[1][0] * 0.5f + o[1][1] * 0.5f;
-        out[p] = r0 * 0.5f + r1 * 0.5f;
-    } else {                               // 320 -> 40: bilinear at 8x+3.5
-        float o[2][2];
-        blur_taps<9, 2, 2>(img, 8 * x + 3, 8 * y + 3, FC.k3, o);
-        float r0 = o[0][0] * 0.5f + o[0][1] * 0.5f, r1 = o[1][0] * 0.5f + o[1][1] * 0.5f;
-        out[p] = r0 * 0.5f + r1 * 0.5f;
+    const float k0[2] = {0.5f, 0.25f};
+    const float *kk = K == 0 ? k0 : (K == 1 ? FC.k1 : (K == 2 ? FC.k2 : FC.k3));
+    for (int i = threadIdx.x; i < T * NC; i += blockDim.x) {
+        const int y = i / NC, ci = i - y * NC;
+        const int xc = ST * (xo0 + ci / N) + OFF + ci % N;
+        t[y][ci] = blur_row<R>(img + (size_t)y * T, xc, kk);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < S * PYR_CW; i += blockDim.x) {
+        const int y = i / PYR_CW, cx = i - y * PYR_CW;
+        const int yc = ST * y + OFF;
+        float o[N][N];
+#pragma unroll
+        for (int oy = 0; oy < N; oy++)
+#pragma unroll
+            for (int ox = 0; ox < N; ox++) {
+                const int c = cx * N + ox, r = yc + oy;
+                float a = kk[0] * t[r][c];
+#pragma unroll
+                for (int j = 1; j <= R; j++) a = a + kk[j] * (t[r101(r - j, T)][c] + t[r101(r + j, T)][c]);
+                o[oy][ox] = a;
+            }
+        float v;
+        if (K == 0) v = o[0][0];
+        else if (K == 1) v = (((o[0][0] + o[0][N - 1]) + o[N - 1][0]) + o[N - 1][N - 1]) * 0.25f;     // 320 -> 160: exact 2x => 2x2 area mean
+        else {                                                                                        // bilinear at the cell centre (weights .5/.5)
+            const float r0 = o[0][0] * 0.5f + o[0][N - 1] * 0.5f, r1 = o[N - 1][0] * 0.5f + o[N - 1][N - 1] * 0.5f;
+            v = r0 * 0.5f + r1 * 0.5f;
+        }
+        out[(size_t)y * S + xo0 + cx] = v;
     }
 }
 
@@ -509,10 +501,10 @@ int k2_flow(avd_ctx *ctx, const uint8_t *d_prev, const uint8_t *d_next, size_t p
             src.mode = 2; src.a = d_prev + (size_t)p0 * prev_stride; src.b = d_next + (size_t)p0 * next_stride;
             src.sa = prev_stride; src.sb = next_stride; mode = 2;
         }
-        AVD_LAUNCH(ctx, "pyr", st, pyr_kernel<3><<<dim3((40 * 40 + 127) / 128, ni), 128, 0, st>>>(src, pyr));
-        AVD_LAUNCH(ctx, "pyr", st, pyr_kernel<2><<<dim3((80 * 80 + 127) / 128, ni), 128, 0, st>>>(src, pyr));
-        AVD_LAUNCH(ctx, "pyr", st, pyr_kernel<1><<<dim3((160 * 160 + 127) / 128, ni), 128, 0, st>>>(src, pyr));
-        AVD_LAUNCH(ctx, "pyr", st, pyr_kernel<0><<<dim3((320 * 320 + 127) / 128, ni), 128, 0, st>>>(src, pyr));
+        AVD_LAUNCH(ctx, "pyr", st, pyr_kernel<3><<<dim3(40 / PYR_CW, ni), 256, 0, st>>>(src, pyr));
+        AVD_LAUNCH(ctx, "pyr", st, pyr_kernel<2><<<dim3(80 / PYR_CW, ni), 256, 0, st>>>(src, pyr));
+        AVD_LAUNCH(ctx, "pyr", st, pyr_kernel<1><<<dim3(160 / PYR_CW, ni), 256, 0, st>>>(src, pyr));
+        AVD_LAUNCH(ctx, "pyr", st, pyr_kernel<0><<<dim3(320 / PYR_CW, ni), 256, 0, st>>>(src, pyr));
         for (int k = 3; k >= 0; k--) {
             int s = lvl_size(k);
             AVD_LAUNCH(ctx, "polyexp", st, polyexp_kernel<<<dim3(s / PE_ROWS, ni), (s + 31) / 32 * 32, 3 * PE_ROWS * (s + 2 * PE_HALO) * sizeof(float), st>>>(pyr, R, k));

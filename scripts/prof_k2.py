@@ -18,3 +18,9 @@ for _ in range(reps):
     eng.flow_stats(thumbs, rec)
 e1.record(); torch.cuda.synchronize()
 print(f"K2 n={n}: {e0.elapsed_time(e1)/reps:.4f} ms per pass, {1e3*e0.elapsed_time(e1)/reps/(n-1):.2f} us/pair")
+eng.profile_read(); eng.profile(True)
+for _ in range(reps):
+    eng.flow_stats(thumbs, rec)
+eng.profile(False)
+for k, v in sorted(eng.profile_read().items(), key=lambda t: -t[1]["ms"]):
+    print(f"  {k:18s} {1e3*v['ms']/reps:8.1f} us/pass  {v['launches']//reps} launches")
