@@ -11,17 +11,20 @@
 // Decomposition: CTA = (frame, band b); band b = the source rows owned by INTER_AREA destination row b plus one
 // halo row above and below (REFLECT_101 rows at the frame edges are simply loaded as the halo).
 //   TMA ring     rows stream into NRS single-row shared-memory stages (cp.async.bulk -> UBLKCP, one mbarrier per
-//                stage); the warp that is LAST to finish reading a stage refills it, nobody waits for a free stage
-//   main warps   a thread owns a 16-pixel column strip (48 bytes = 3 conflict-free LDS.128) and marches down the
+//                stage); the warp that is LAST to finish reading a stage (mbarrier arrive + pending count) refills it
+//                from registers, nobody waits for a free stage; the next stage's barrier is probed a row ahead
+//   threads      a thread owns a 16-pixel column strip (48 bytes = 3 conflict-free LDS.128) and marches down the
 //                band keeping three rows in registers (straight-line code, three rotating register sets):
 //                gray        2 IDP.2A per pixel (15-bit weights doubled so that Y lands in byte 2)
 //                Laplacian   two pixels per register in 16-bit lanes, biased by +1020; sum of squares through
 //                            byte-split IDP.4A; the plain sum telescopes to strip/band borders
 //                INTER_AREA  exact integer cell sums (one IADD3 per 4 pixels) -- see "certificate" below
 //                thumbnail   the thread that owns a strip also owns the thumbnail columns whose left tap lies in
-//                            it: on tap rows it parks its 16 gray bytes (+ the right neighbour) in a private
-//                            48-byte shared-memory slot and reads the tap bytes back at its own dynamic offsets --
-//                            thread-private, so the warps never meet a block barrier inside the band
+//                            it; tap values pass through a private 48-byte shared-memory slot (which register holds
+//                            a given tap differs from thread to thread; the slot offset is per-thread data) or, for
+//                            W = 1280 / 2560, come straight out of the registers.  Thread-private, so the warps never
+//                            meet a block barrier inside the band; the band's thumbnail rows are staged in shared
+//                            memory and written out by its last warp.
 //
 // INTER_AREA certificate.  The library accumulates float32 products sequentially; the result is
 // rounded to u8 and only that byte is observable.  The kernel computes the exact rational cell mean from integer
@@ -31,34 +34,14 @@
 // round(mean).  The few cells (~0.2 %) that are closer are listed and recomputed in the library's exact float32
 // order by area_fix_kernel (k1_generic.cu), off this kernel's critical path.
 #include "avd_internal.h"
-#include <stdio.h>
-#include <stdlib.h>
 
 namespace {
 
 #ifndef K1_NRS
 #define K1_NRS 6
 #endif
-#ifndef K1_OPAQUE
-#define K1_OPAQUE 1
-#endif
-#ifndef K1_OPAQUE_BASE
-#define K1_OPAQUE_BASE 1
-#endif
 #ifndef K1_NOTHUMB
 #define K1_NOTHUMB 0
-#endif
-#ifndef K1_NOFIX
-#define K1_NOFIX 0
-#endif
-#ifndef K1_ISSUE_INLINE
-#define K1_ISSUE_INLINE __forceinline__
-#endif
-#ifndef K1_BANDPAR
-#define K1_BANDPAR 0
-#endif
-#ifndef K1_STUB
-#define K1_STUB 0
 #endif
 #ifndef K1_MINB
 #define K1_MINB 4
@@ -71,7 +54,7 @@ constexpr int MAX_TROWS = 16;         // thumbnail rows a band can own (staged i
 constexpr int SLOT = 48;              // bytes of a thread's private gray slot (48: conflict-free 128-bit stores)
 
 // shared-memory header (bytes)
-constexpr int OFF_FULL = 0, OFF_CNT = 64, OFF_PAR = 128, OFF_MISC = 192, OFF_CELL = 256, OFF_RED = 384, OFF_INFO = 512, HDR = 1040;
+constexpr int OFF_FULL = 0, OFF_CNT = 64, OFF_MISC = 192, OFF_CELL = 256, OFF_INFO = 512, HDR = 1040;
 static_assert(OFF_INFO + 4 * MAXQ <= HDR, "header layout");
 
 struct K1Params {
@@ -146,10 +129,6 @@ struct GrayK {
     uint32_t bg, r0, ob, gr, rnd;
     __device__ __forceinline__ void load()
     {
-#if !K1_OPAQUE
-        bg = C_BG; r0 = C_R0; ob = C_0B; gr = C_GR; rnd = RND;
-        return;
-#endif
         asm volatile("mov.u32 %0, %1;" : "=r"(bg) : "n"(C_BG)); asm volatile("mov.u32 %0, %1;" : "=r"(r0) : "n"(C_R0));
         asm volatile("mov.u32 %0, %1;" : "=r"(ob) : "n"(C_0B)); asm volatile("mov.u32 %0, %1;" : "=r"(gr) : "n"(C_GR));
         asm volatile("mov.u32 %0, %1;" : "=r"(rnd) : "n"(RND));
@@ -186,12 +165,10 @@ struct Band {
     uint32_t stage;                       // shared address of stage 0
     uint32_t slot;                        // shared address of this thread's private gray slot
     int row_bytes, nseq;
-#if !K1_BANDPAR
     int H, own0;
     const uint8_t *frame;
     size_t pitch;
     uint64_t pol_stream, pol_keep;
-#endif
     GrayK K;
     int todd;                             // pair-sum thumbnail: tap pairs start at odd offsets
 };
@@ -261,10 +238,6 @@ __device__ __forceinline__ void thumb_pairs_end(const Thumb<JT> &T, uint32_t inf
 template <int JT, int TM>
 __device__ __forceinline__ void lap_step(const Band &B, const RowSet &U, const RowSet &C, const RowSet &D, Acc &A, Thumb<JT> &T, uint32_t infoC)
 {
-#if K1_STUB
-    A.ll += U.E[0] + C.E[1] + D.E[2] + C.E[3] + C.O[0] + C.LR;
-    return;
-#endif
     uint32_t el[4], orr[4], Pp[4];
 #pragma unroll
     for (int g = 0; g < 4; g++) {
@@ -301,22 +274,7 @@ __device__ __forceinline__ void lap_step(const Band &B, const RowSet &U, const R
 #endif
 }
 
-// What the out-of-line helpers (row refill, cell fix-up) need, kept in shared memory so that calling them costs the
-// hot loop no registers (they run in one lane / one warp, rarely).
-struct BandPar {
-    const uint8_t *frame;
-    unsigned long long pitch, pol_stream, pol_keep;
-    const ShapeTables *tab;
-    int row_bytes, own0, H, nseq;
-};
-static_assert(sizeof(BandPar) <= OFF_MISC - OFF_PAR, "header layout");
-__device__ __forceinline__ const BandPar *band_par(uint32_t sbase)
-{
-    return (const BandPar *)__cvta_shared_to_generic((size_t)(sbase + OFF_PAR));
-}
-
 // sequence row q of the band = source row own0-1+q, reflected at the frame edges (BORDER_REFLECT_101)
-#if !K1_BANDPAR
 __device__ __forceinline__ void issue_row(const Band &B, int q, int s)
 {
     int r = B.own0 - 1 + q;
@@ -326,19 +284,6 @@ __device__ __forceinline__ void issue_row(const Band &B, int q, int s)
     // the two first and two last rows of a band are also read by the neighbouring bands: do not mark them evict-first
     const bool shared_row = q < 2 || q >= B.nseq - 2;
     tma_load_1d(B.stage + s * B.row_bytes, B.frame + (size_t)r * B.pitch, (uint32_t)B.row_bytes, bar, shared_row ? B.pol_keep : B.pol_stream);
-}
-#endif
-__device__ K1_ISSUE_INLINE void issue_row(uint32_t sbase, int q, int s)
-{
-    const BandPar *bp = band_par(sbase);
-    int r = bp->own0 - 1 + q;
-    r = r < 0 ? 1 : (r >= bp->H ? bp->H - 2 : r);
-    const uint32_t bar = sbase + OFF_FULL + 8 * s;   // s = 3 * group + position
-    mbar_expect_tx(bar, (uint32_t)bp->row_bytes);
-    // the two first and two last rows of a band are also read by the neighbouring bands: do not mark them evict-first
-    const bool shared_row = q < 2 || q >= bp->nseq - 2;
-    tma_load_1d(sbase + HDR + s * bp->row_bytes, bp->frame + (size_t)r * bp->pitch, (uint32_t)bp->row_bytes, bar,
-                shared_row ? bp->pol_keep : bp->pol_stream);
 }
 
 // Stage s holds sequence row q: convert this thread's strip to gray (row set R); on tap rows of the thumbnail also
@@ -360,15 +305,6 @@ __device__ __forceinline__ uint32_t load_row(const Band &B, int q, int grp, uint
     asm volatile("ld.shared.u32 %0, [%1+48];" : "=r"(wr) : "r"(sp));
     uint32_t a[16];
     const GrayK &K = B.K;
-#if K1_STUB
-    // timing experiment only: the streaming skeleton without the arithmetic
-    R.E[0] = q0.x ^ q1.x ^ q2.x; R.E[1] = q0.y ^ q1.y ^ q2.y; R.E[2] = q0.z ^ q1.z ^ q2.z; R.E[3] = q0.w ^ q1.w ^ q2.w;
-    R.O[0] = R.O[1] = R.O[2] = R.O[3] = wl; R.LR = wr;
-    __syncwarp();
-    const uint32_t ticket0 = stage_arrive(B.sbase + OFF_CNT + 8 * S, (tid & 31) == 0 ? 1u : 0u, wl ^ wr);
-    ok = mbar_try(nbar, npar);
-    return ticket0;
-#endif
     gray4(K, q0.x, q0.y, q0.z, a[0], a[1], a[2], a[3]);
     gray4(K, q0.w, q1.x, q1.y, a[4], a[5], a[6], a[7]);
     gray4(K, q1.z, q1.w, q2.x, a[8], a[9], a[10], a[11]);
@@ -428,11 +364,7 @@ __device__ __forceinline__ uint32_t load_row(const Band &B, int q, int grp, uint
 template <int POS>
 __device__ __forceinline__ void release_finish(const Band &B, int q, int grp, uint32_t ticket)
 {
-#if K1_BANDPAR
-    if (ticket == 1u && q + NRS < B.nseq) issue_row(B.sbase, q + NRS, 3 * grp + POS);
-#else
     if (ticket == 1u && q + NRS < B.nseq) issue_row(B, q + NRS, 3 * grp + POS);
-#endif
 }
 
 __device__ __forceinline__ uint8_t sat_rne(float v)
@@ -462,11 +394,7 @@ __global__ void __launch_bounds__(MAXT, MINB) k1_fused_kernel(K1Params P)
     const int own0 = tab->row_owner_begin[b], own1 = tab->row_owner_begin[b + 1];
     const int n = own1 - own0, nseq = n + 2;
     uint32_t sbase;                         // opaque, or the compiler recomputes the shared window address at every use
-#if K1_OPAQUE_BASE
     asm volatile("mov.u32 %0, %1;" : "=r"(sbase) : "r"(smem_u32(smem)));
-#else
-    sbase = smem_u32(smem);
-#endif
     const uint8_t *frame = P.bgr + (size_t)f * P.fstride;
 
     Band B;
@@ -474,31 +402,18 @@ __global__ void __launch_bounds__(MAXT, MINB) k1_fused_kernel(K1Params P)
     B.row_bytes = P.row_bytes; B.nseq = nseq;
     B.K.load();
     B.todd = tab->lx[0].i0 & 1;
-#if !K1_BANDPAR
     B.H = H; B.own0 = own0; B.frame = frame; B.pitch = P.pitch;
     asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(B.pol_stream));
     asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(B.pol_keep));
-#endif
 
     if (tid == 0) {
         for (int s = 0; s < NRS; s++) {
             mbar_init(sbase + OFF_FULL + 8 * s, 1);
             mbar_init(sbase + OFF_CNT + 8 * s, nw);
         }
-        BandPar *bp = (BandPar *)(smem + OFF_PAR);
-        unsigned long long pol_stream, pol_keep;
-        asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol_stream));
-        asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(pol_keep));
-        bp->frame = frame; bp->pitch = P.pitch; bp->pol_stream = pol_stream; bp->pol_keep = pol_keep; bp->tab = tab;
-        bp->row_bytes = P.row_bytes; bp->own0 = own0; bp->H = H; bp->nseq = nseq;
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-#if K1_BANDPAR
-#pragma unroll 1
-        for (int q = 0; q < NRS; q++) issue_row(sbase, q, q);
-#else
         for (int q = 0; q < NRS; q++) issue_row(B, q, q);
-#endif
     }
     if (tid < 32) ((int *)(smem + OFF_CELL))[tid] = 0;
     if (tid == 32) ((uint32_t *)(smem + OFF_MISC))[1] = 0;          // warps that finished the band
@@ -568,7 +483,7 @@ __global__ void __launch_bounds__(MAXT, MINB) k1_fused_kernel(K1Params P)
         return v;
     };
     auto band_end = [&](const RowSet &C, const RowSet &D) {
-#if !K1_NOTHUMB && !K1_STUB
+#if !K1_NOTHUMB
         const uint32_t infoD = row_info(nseq - 1);       // the bottom halo row is never a centre row
         if ((TM != 0) && (infoD & 2u)) {
             uint32_t orrC[4], orrD[4], XU[4], XC[4], s0[JT], s1[JT];
@@ -710,11 +625,6 @@ static int k1_launch(avd_ctx *ctx, const K1Params &P, int n, size_t smem, int th
         Q.bgr = P.bgr + (size_t)f0 * P.fstride; Q.rec = P.rec + f0;
         Q.thumbs = P.thumbs + (size_t)f0 * AVD_T * AVD_T; Q.area32 = P.area32 + (size_t)f0 * 1024;
         Q.frame0 = f0;
-        if (getenv("AVD_DEBUG")) {
-            cudaFuncAttributes fa; cudaFuncGetAttributes(&fa, k1_fused_kernel<MAXT, MINB, JT, TM>);
-            fprintf(stderr, "k1_launch<%d,%d,%d,%d>: threads %d smem %zu | maxThreads %d regs %d maxDyn %d static %zu\n", MAXT, MINB, JT, TM, threads, smem,
-                    fa.maxThreadsPerBlock, fa.numRegs, fa.maxDynamicSharedSizeBytes, fa.sharedSizeBytes);
-        }
         AVD_LAUNCH(ctx, "k1_fused", st, (k1_fused_kernel<MAXT, MINB, JT, TM><<<dim3(AVD_D, nb), threads, smem, st>>>(Q)));
     }
     return AVD_OK;
