@@ -27,9 +27,14 @@ class Engine:
             raise AvdError(f"avd_create(device={device}) failed with status {rc} (needs an sm_100 GPU)")
         self.h, self.device = h, int(device)
         self._lock = threading.Lock()   # a context is single-threaded (include/avd.h)
+        self._graphs = {}
 
     # -- plumbing ------------------------------------------------------------------------------------
+    graph_launches = 0           # kernel launches replayed through CUDA graphs (not seen by avd_launch_count)
+
     def close(self):
+        if self._graphs:
+            self._graphs.clear()
         if getattr(self, "h", None):
             self.L.avd_destroy(self.h)
             self.h = None
@@ -134,6 +139,31 @@ class Engine:
             rec, thumbs = self.frames_features(frames)
             self.flow_stats(thumbs, rec)
         return rec
+
+    def analyze_device_graph(self, frames, prev_frame=None):
+        """analyze_device through a CUDA graph: the ~40 kernel launches of the device path are captured once per
+        (buffers, shape) and replayed, which removes most of the launch gaps between the small Farneback kernels.
+        The inputs must stay at the same addresses between calls (a resident batch, a reused staging buffer); the
+        returned record tensor is owned by the graph and overwritten by the next call."""
+        import torch
+        key = (frames.data_ptr(), tuple(frames.shape), tuple(frames.stride()),
+               None if prev_frame is None else prev_frame.data_ptr())
+        g = self._graphs.get(key)
+        if g is None:
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                self.analyze_device(frames, prev_frame)      # warm-up: tables, workspaces, function attributes
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+            graph = torch.cuda.CUDAGraph()
+            l0 = self.launches
+            with torch.cuda.graph(graph):
+                rec = self.analyze_device(frames, prev_frame)
+            g = self._graphs[key] = (graph, rec, self.launches - l0)
+        g[0].replay()
+        self.graph_launches += g[2]
+        return g[1]
 
     @staticmethod
     def records_to_numpy(rec) -> np.ndarray:

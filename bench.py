@@ -209,8 +209,12 @@ def main():
         res = video.result_from_records(recs_np, H, W, FPS, meta["duration"], w=W, h=H)
         return fusion.fuse(fusion.neutral_audio(len(res["timeline"])), res, hnt)
 
-    def step_device():
-        rec = eng.analyze_device(d_frames, prev_frame=d_halo)
+    use_graph = os.environ.get("AVD_BENCH_GRAPH", "1") != "0"
+
+    def step_device(graph=None):
+        # the device path replays a CUDA graph of its ~40 launches (Engine.analyze_device_graph); the per-kernel
+        # profiling pass below runs the plain launches
+        rec = (eng.analyze_device_graph if (use_graph if graph is None else graph) else eng.analyze_device)(d_frames, prev_frame=d_halo)
         if world > 1:
             dist.all_gather_into_tensor(recv, rec)
             rec = recv
@@ -240,7 +244,7 @@ def main():
         barrier()
         if prof:
             eng.profile_read(); eng.profile(True)
-        l0 = eng.launches
+        l0 = eng.launches + eng.graph_launches
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         t0 = time.perf_counter()
         e0.record()
@@ -257,7 +261,7 @@ def main():
         t = torch.tensor([max(ms / 1e3, wall)], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item()), eng.launches - l0, kern, out
+        return float(t.item()), eng.launches + eng.graph_launches - l0, kern, out
 
     for _ in range(args.warmup):
         step_device()
@@ -265,7 +269,7 @@ def main():
     dt, launches, _, result = timed(step_device, args.steps)
     clocks = sampler.result()
     # same loop again with per-launch CUDA events on (kept out of `value`: the events add ~1 us per launch)
-    _, _, kern, _ = timed(step_device, args.steps, prof=True)
+    _, _, kern, _ = timed(lambda: step_device(graph=False), args.steps, prof=True)
     for _ in range(args.warmup):
         step_host()
     dt_e2e, _, _, result_e2e = timed(step_host, args.steps)
@@ -286,7 +290,8 @@ def main():
             "scaling": "weak", "vs_baseline": None, "dtype": "u8 (K1 integer path) / f32+f64 (Farneback)", "data": "synthetic",
             "config": {"workload": "1080p 30fps 60s synthetic clip (1800 frames -> 120 sampled frames) per GPU: per-frame features + 119 flow pairs + timeline/fuse",
                        "frames_per_step_per_gpu": SAMPLES, "sharding": "none" if world == 1 else f"frame-chunk x{world}, 1-sample halo, all-gather of 160 B records",
-                       "l2_policy": "inputs (746 MB/GPU) larger than L2 (126 MB), no flush needed", "seed": SEED},
+                       "l2_policy": "inputs (746 MB/GPU) larger than L2 (126 MB), no flush needed", "seed": SEED,
+                       "device_path": "CUDA graph replay of the step's kernel launches" if use_graph else "plain stream launches"},
             "clocks": clocks, "gpu_launches": int(launches),
             "e2e": {"value": n_total * args.steps / dt_e2e, "unit": "frames/s", "h2d_bytes_per_step": int(FRAME_BYTES * (SAMPLES * world + world - 1)),
                     "d2h_bytes_per_step": int(160 * n_total), "ms_per_step": 1e3 * dt_e2e / args.steps},

@@ -323,3 +323,19 @@ def test_edge_cases_and_errors(torch, eng):
     with pytest.raises(AvdError):
         eng.analyze_host([np.zeros((64, 64, 3), np.uint8), np.zeros((64, 65, 3), np.uint8)])
     assert len(eng.analyze_host([np.zeros((40, 50, 3), np.uint8)])) == 1   # engine still usable after errors
+
+
+def test_device_path_graph_replay_equals_plain_launches(synth, torch, eng):
+    """Engine.analyze_device_graph (CUDA graph of the step's launches) must return the same records as the plain
+    launches, on first use (capture) and on replays with new frame contents at the same addresses, with and
+    without a chunk halo."""
+    clip = synth.Clip(40, 720, 1280, seed=21, events=True)
+    frames = torch.from_numpy(np.stack([clip[i] for i in range(0, 40, 4)])).cuda()
+    halo = torch.from_numpy(clip[39]).cuda()
+    for prev in (None, halo):
+        for rnd in range(3):
+            if rnd:
+                frames.copy_(torch.from_numpy(np.stack([clip[(i + 7 * rnd) % 40] for i in range(0, 40, 4)])))
+            want = eng.analyze_device(frames, prev_frame=prev).cpu().numpy().tobytes()
+            got = eng.analyze_device_graph(frames, prev_frame=prev).cpu().numpy().tobytes()
+            assert got == want, (prev is not None, rnd)
