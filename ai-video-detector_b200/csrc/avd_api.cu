@@ -388,7 +388,7 @@ int avd_analyze_host(avd_ctx *ctx, const uint8_t *const *h_frames, int n, int H,
     size_t dpitch = ((size_t)W * 3 + 15) & ~(size_t)15;
     size_t fbytes = dpitch * H;
     const int SLOTS = 3;
-    int per_slot = (int)((48u << 20) / fbytes);
+    int per_slot = (int)((112u << 20) / fbytes);
     if (per_slot < 1) per_slot = 1;
     static const int max_slot = getenv("AVD_HOST_CHUNK") ? atoi(getenv("AVD_HOST_CHUNK")) : 16;   // frames per device slot (tuning)
     if (per_slot > max_slot) per_slot = max_slot < 1 ? 1 : max_slot;
@@ -405,13 +405,20 @@ int avd_analyze_host(avd_ctx *ctx, const uint8_t *const *h_frames, int n, int H,
         int slot = chunk % SLOTS;
         uint8_t *dst = ctx->ring + (size_t)slot * per_slot * fbytes;
         if (chunk >= SLOTS) AVD_CUDA(ctx, cudaStreamWaitEvent(ctx->copy, ctx->ev_free[slot], 0));
-        for (int j = 0; j < nb; j++) {
+        for (int j = 0; j < nb; j++)
             if (!h_frames[f0 + j]) { ctx->err = "null frame pointer"; cudaStreamSynchronize(ctx->copy); cudaStreamSynchronize(ctx->compute); return AVD_ERR_ARG; }
-            if (dpitch == row_pitch)
-                AVD_CUDA(ctx, cudaMemcpyAsync(dst + (size_t)j * fbytes, h_frames[f0 + j], fbytes, cudaMemcpyHostToDevice, ctx->copy));
-            else
+        for (int j = 0; j < nb;) {
+            if (dpitch == row_pitch) {
+                // frames that sit back to back in host memory (one decoded batch) go as one copy: fewer, larger DMA requests
+                int run = 1;
+                while (j + run < nb && h_frames[f0 + j + run] == h_frames[f0 + j + run - 1] + fbytes) run++;
+                AVD_CUDA(ctx, cudaMemcpyAsync(dst + (size_t)j * fbytes, h_frames[f0 + j], fbytes * run, cudaMemcpyHostToDevice, ctx->copy));
+                j += run;
+            } else {
                 AVD_CUDA(ctx, cudaMemcpy2DAsync(dst + (size_t)j * fbytes, dpitch, h_frames[f0 + j], row_pitch, (size_t)W * 3, H,
                                                cudaMemcpyHostToDevice, ctx->copy));
+                j++;
+            }
         }
         AVD_CUDA(ctx, cudaEventRecord(ctx->ev_copied[slot], ctx->copy));
         AVD_CUDA(ctx, cudaStreamWaitEvent(ctx->compute, ctx->ev_copied[slot], 0));
