@@ -108,7 +108,7 @@ class ClockSampler(threading.Thread):
                     self.samples.append(int(o[0])); self.max_mhz = int(o[1])
             except Exception:
                 pass
-            time.sleep(0.05)
+            time.sleep(0.004)
 
     def result(self):
         self.stop_flag = True
@@ -267,12 +267,16 @@ def main():
         step_device()
     sampler = ClockSampler(local_rank); sampler.start()
     dt, launches, _, result = timed(step_device, args.steps)
-    clocks = sampler.result()
+    clocks_dev = sampler.result()
     # same loop again with per-launch CUDA events on (kept out of `value`: the events add ~1 us per launch)
     _, _, kern, _ = timed(lambda: step_device(graph=False), args.steps, prof=True)
     for _ in range(args.warmup):
         step_host()
+    sampler = ClockSampler(local_rank); sampler.start()
     dt_e2e, _, _, result_e2e = timed(step_host, args.steps)
+    clocks_e2e = sampler.result()
+    clocks = dict(clocks_dev, samples_e2e=clocks_e2e["samples"], sm_mhz_e2e=clocks_e2e["sm_mhz"],
+                  reasons=sorted(set(clocks_dev["reasons"]) | set(clocks_e2e["reasons"])))
 
     if rank == 0:
         value = n_total * args.steps / dt
