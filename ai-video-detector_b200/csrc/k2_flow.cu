@@ -348,9 +348,11 @@ __global__ void __launch_bounds__(32 * BX_WARPS) box_solve_kernel(const float *_
                     sm += mag; sq += mag * mag;
                 }
             }
-            float *fo = flow + (size_t)p * 2 * plane + (size_t)y * s + xb;
-            *(float4 *)fo = make_float4(fx[0], fx[1], fx[2], fx[3]);
-            *(float4 *)(fo + plane) = make_float4(fy[0], fy[1], fy[2], fy[3]);
+            if (!STATS) {        // the statistics launch is the last of the chain: nobody reads its flow field
+                float *fo = flow + (size_t)p * 2 * plane + (size_t)y * s + xb;
+                *(float4 *)fo = make_float4(fx[0], fx[1], fx[2], fx[3]);
+                *(float4 *)(fo + plane) = make_float4(fy[0], fy[1], fy[2], fy[3]);
+            }
         }
         // slide the vertical window: + row y+8, - row y-7 (replicated borders)
         const float *rn = M + (size_t)min(y + BS_M + 1, s - 1) * s, *ro = M + (size_t)max(y - BS_M, 0) * s;
@@ -480,6 +482,7 @@ int k2_flow(avd_ctx *ctx, const uint8_t *d_prev, const uint8_t *d_next, size_t p
         consts_done[ctx->device & 63] = true;
     }
     if (n_pairs <= 0) return AVD_OK;
+    if (d_rec_first && d_flow_out) { ctx->err = "k2_flow: statistics and dense fields are separate calls"; return AVD_ERR_ARG; }
     const int MAXP = 128;   // pairs per batch
     int rc;
     int cap_np = n_pairs < MAXP ? n_pairs : MAXP, cap_ni = shared_chain ? cap_np + 1 : 2 * cap_np;
