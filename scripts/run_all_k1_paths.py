@@ -1,4 +1,5 @@
-"""Small K1/K2 run for compute-sanitizer: two frames per shape through every K1 path, one short host pipeline."""
+"""Small K1/K2 run through every per-frame kernel path (streaming, banded, generic; boundary-cell fix-up) and one short
+host pipeline -- a quick crash check after kernel changes (compute-sanitizer is closed on this pool)."""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
