@@ -370,6 +370,137 @@ __global__ void __launch_bounds__(32 * BX_WARPS) box_solve_kernel(const float *_
     }
 }
 
+// ---- box_solve with an asynchronous row ring ---------------------------------------------------------------
+// Same arithmetic as box_solve_kernel, different data movement: every lane copies the rows it is going to need into its
+// own shared-memory ring with cp.async (LDGSTS), BXR-1 steps ahead, instead of holding them in registers; a lane only
+// ever reads what it copied itself, so the only synchronisation is cp.async.wait_group.  Measured (119 pairs, all 12
+// launches): direct loads 878 us, ring depth 2: 851 us, 3: 917 us, 4: 948 us, 6: 1379 us -- the kernel lives on resident
+// warps, not on prefetch distance, so the shallowest ring (40 KB per CTA, 4 CTAs per SM) is the default.
+// Step i < 15 brings window row y0-7+i; step 15+j brings the row that enters (y0+8+j) and the row that leaves (y0-7+j).
+#ifndef K2_BXR
+#define K2_BXR 2
+#endif
+constexpr int BXR = K2_BXR;                                   // ring depth (steps)
+constexpr int BXR_FLOAT4_PER_WARP = 2 * BXR * 5 * 32;    // 2 streams x ring x 5 channels x 32 lanes
+__device__ __forceinline__ void cp_async16(float4 *dst, const float *src)
+{
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ float4 edge_fix(float4 q, int xb, int s)
+{
+    if (xb < 0) q = make_float4(q.x, q.x, q.x, q.x);
+    else if (xb >= s) q = make_float4(q.w, q.w, q.w, q.w);
+    return q;
+}
+
+template <bool STATS>
+__global__ void __launch_bounds__(32 * BX_WARPS) box_solve_ring_kernel(const float *__restrict__ Mall, float *__restrict__ flow, int k, int BX_SEG,
+                                                                      int n_pairs, double *__restrict__ task_stats, int p_base)
+{
+    extern __shared__ float4 bx_ring[];
+    const int s = lvl_size(k);
+    const int lane = threadIdx.x & 31;
+    const int tasks_per_pair = bx_strips(s) * bx_segs(s, BX_SEG);
+    const int task = blockIdx.x * BX_WARPS + (threadIdx.x >> 5);
+    if (task >= tasks_per_pair * n_pairs) return;
+    const int pl = task / tasks_per_pair, tp = task - pl * tasks_per_pair, p = pl + p_base;
+    const int strip = tp % bx_strips(s), seg = tp / bx_strips(s);
+    const int xb = strip * BX_COLS - 8 + 4 * lane, xa = clampi(xb, 0, s - 4);
+    const int y0 = seg * BX_SEG, y1 = min(y0 + BX_SEG, s), nout = y1 - y0;
+    const size_t plane = (size_t)s * s;
+    const float *M = Mall + (size_t)p * 5 * T * T + xa;
+    const bool out_lane = lane >= 2 && lane < 30 && xb >= 0 && xb < s;
+    float4 *ring = bx_ring + (threadIdx.x >> 5) * BXR_FLOAT4_PER_WARP + lane;
+    const int nsteps = 15 + nout - 1;
+
+    auto issue = [&](int i) {
+        if (i < nsteps) {
+            float4 *slot = ring + (i % BXR) * 5 * 32;
+            const float *ra = M + (size_t)clampi(y0 - BS_M + i, 0, s - 1) * s;
+#pragma unroll
+            for (int c = 0; c < 5; c++) cp_async16(slot + c * 32, ra + c * plane);
+            if (i >= 15) {
+                const float *rs = M + (size_t)max(y0 - BS_M + i - 15, 0) * s;
+#pragma unroll
+                for (int c = 0; c < 5; c++) cp_async16(slot + (BXR * 5 + c) * 32, rs + c * plane);
+            }
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+#pragma unroll
+    for (int i = 0; i < BXR - 1; i++) issue(i);
+
+    double run[5][4];
+#pragma unroll
+    for (int c = 0; c < 5; c++) { run[c][0] = run[c][1] = run[c][2] = run[c][3] = 0.0; }
+    for (int i = 0; i < 15; i++) {
+        issue(i + BXR - 1);
+        asm volatile("cp.async.wait_group %0;" ::"n"(BXR - 1) : "memory");
+        const float4 *slot = ring + (i % BXR) * 5 * 32;
+#pragma unroll
+        for (int c = 0; c < 5; c++) {
+            const float4 q = edge_fix(slot[c * 32], xb, s);
+            run[c][0] += (double)q.x; run[c][1] += (double)q.y; run[c][2] += (double)q.z; run[c][3] += (double)q.w;
+        }
+    }
+    const double scale = 1.0 / 225.0;
+    double sm = 0, sq = 0;
+    for (int j = 0; j < nout; j++) {
+        const int y = y0 + j;
+        double a[5][4];
+#pragma unroll
+        for (int c = 0; c < 5; c++) {
+            const double v0 = run[c][0], v1 = run[c][1], v2 = run[c][2], v3 = run[c][3];
+            const double tot = (v0 + v1) + (v2 + v3);
+            const double mid = __shfl_up_sync(0xffffffffu, tot, 1) + tot + __shfl_down_sync(0xffffffffu, tot, 1);
+            const double l1 = __shfl_up_sync(0xffffffffu, v1, 2), l2 = __shfl_up_sync(0xffffffffu, v2, 2), l3 = __shfl_up_sync(0xffffffffu, v3, 2);
+            const double r0 = __shfl_down_sync(0xffffffffu, v0, 2), r1 = __shfl_down_sync(0xffffffffu, v1, 2), r2 = __shfl_down_sync(0xffffffffu, v2, 2);
+            const double s3 = l3, s2 = l2 + l3, s1 = l1 + s2;       // suffix sums of lane t-2 from local index 3,2,1
+            const double p1 = r0, p2 = r0 + r1, p3 = p2 + r2;       // prefix sums of lane t+2 of 1,2,3 columns
+            a[c][0] = (mid + s1) * scale;
+            a[c][1] = (mid + s2 + p1) * scale;
+            a[c][2] = (mid + s3 + p2) * scale;
+            a[c][3] = (mid + p3) * scale;
+        }
+        if (out_lane) {
+            float fx[4], fy[4];
+#pragma unroll
+            for (int jj = 0; jj < 4; jj++) {
+                const double g11 = a[0][jj], g12 = a[1][jj], g22 = a[2][jj], h1 = a[3][jj], h2 = a[4][jj];
+                const double idet = 1.0 / (g11 * g22 - g12 * g12 + 1e-3);
+                fx[jj] = (float)((g11 * h2 - g12 * h1) * idet);
+                fy[jj] = (float)((g22 * h1 - g12 * h2) * idet);
+                if (STATS) {
+                    const double mag = (double)sqrtf(fx[jj] * fx[jj] + fy[jj] * fy[jj]);   // float32 magnitude like np.sqrt(fx**2+fy**2)
+                    sm += mag; sq += mag * mag;
+                }
+            }
+            if (!STATS) {        // the statistics launch is the last of the chain: nobody reads its flow field
+                float *fo = flow + (size_t)p * 2 * plane + (size_t)y * s + xb;
+                *(float4 *)fo = make_float4(fx[0], fx[1], fx[2], fx[3]);
+                *(float4 *)(fo + plane) = make_float4(fy[0], fy[1], fy[2], fy[3]);
+            }
+        }
+        if (j + 1 < nout) {
+            // slide the vertical window: + row y+8, - row y-7 (replicated borders)
+            const int i = 15 + j;
+            issue(i + BXR - 1);
+            asm volatile("cp.async.wait_group %0;" ::"n"(BXR - 1) : "memory");
+            const float4 *slot = ring + (i % BXR) * 5 * 32;
+#pragma unroll
+            for (int c = 0; c < 5; c++) {
+                const float4 qn = edge_fix(slot[c * 32], xb, s), qo = edge_fix(slot[(BXR * 5 + c) * 32], xb, s);
+                run[c][0] += (double)qn.x - (double)qo.x; run[c][1] += (double)qn.y - (double)qo.y;
+                run[c][2] += (double)qn.z - (double)qo.z; run[c][3] += (double)qn.w - (double)qo.w;
+            }
+        }
+    }
+    if (STATS) {
+        for (int o = 16; o; o >>= 1) { sm += __shfl_down_sync(0xffffffffu, sm, o); sq += __shfl_down_sync(0xffffffffu, sq, o); }
+        if (lane == 0) { size_t t = (size_t)p * tasks_per_pair + tp; task_stats[2 * t] = sm; task_stats[2 * t + 1] = sq; }
+    }
+}
+
 // mean / variance of |flow| from the per-tile partial sums (fixed order => bit-reproducible)
 __global__ void magstats_finalize_kernel(const double *__restrict__ tile_stats, int tiles, avd_sample_rec *rec, int n_pairs)
 {
@@ -524,6 +655,14 @@ int k2_flow(avd_ctx *ctx, const uint8_t *d_prev, const uint8_t *d_next, size_t p
             for (int &v : seg_rows) v = v < BX_MIN_SEG ? BX_MIN_SEG : v;
             seg_init = true;
         }
+        static const bool box_ring = !(getenv("AVD_K2_BOXRING") && atoi(getenv("AVD_K2_BOXRING")) == 0);
+        static bool ring_attr[64] = {};
+        if (box_ring && !ring_attr[ctx->device & 63]) {
+            const int bytes = (int)(BX_WARPS * BXR_FLOAT4_PER_WARP * sizeof(float4));
+            AVD_CUDA(ctx, cudaFuncSetAttribute(box_solve_ring_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+            AVD_CUDA(ctx, cudaFuncSetAttribute(box_solve_ring_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+            ring_attr[ctx->device & 63] = true;
+        }
         static int sb0 = getenv("AVD_K2_SB0") ? atoi(getenv("AVD_K2_SB0")) : 0, sb1 = getenv("AVD_K2_SB1") ? atoi(getenv("AVD_K2_SB1")) : 0;
         for (int k = 3; k >= 0; k--) {
             const int s = lvl_size(k);
@@ -539,7 +678,14 @@ int k2_flow(avd_ctx *ctx, const uint8_t *d_prev, const uint8_t *d_next, size_t p
                     AVD_LAUNCH(ctx, "update_matrices", st, update_matrices_kernel<2><<<gu, bu, 0, st>>>(R, nullptr, prev, M, nullptr, k, mode, q0));
                 }
                 for (int it = 0; it < 3; it++) {
-                    if (k == 0 && it == 2 && d_rec_first) {
+                    const size_t ring_bytes = (size_t)BX_WARPS * BXR_FLOAT4_PER_WARP * sizeof(float4);
+                    if (box_ring) {
+                        if (k == 0 && it == 2 && d_rec_first) {
+                            AVD_LAUNCH(ctx, "box_solve", st, box_solve_ring_kernel<true><<<bx_blocks, 32 * BX_WARPS, ring_bytes, st>>>(M, cur, k, seg, nq, tile_stats, q0));
+                        } else {
+                            AVD_LAUNCH(ctx, "box_solve", st, box_solve_ring_kernel<false><<<bx_blocks, 32 * BX_WARPS, ring_bytes, st>>>(M, cur, k, seg, nq, nullptr, q0));
+                        }
+                    } else if (k == 0 && it == 2 && d_rec_first) {
                         AVD_LAUNCH(ctx, "box_solve", st, box_solve_kernel<true><<<bx_blocks, 32 * BX_WARPS, 0, st>>>(M, cur, k, seg, nq, tile_stats, q0));
                     } else {
                         AVD_LAUNCH(ctx, "box_solve", st, box_solve_kernel<false><<<bx_blocks, 32 * BX_WARPS, 0, st>>>(M, cur, k, seg, nq, nullptr, q0));

@@ -2,5 +2,5 @@
 # time every built K2 variant: scripts/ab_k2.sh n reps [name-filter]
 cd "$(dirname "$0")/.."
 for so in ai-video-detector_b200/csrc/variants/libavd_${3:-}*.so; do
-  echo -n "$(basename $so): "; AVD_LIB=$PWD/$so python scripts/prof_k2.py $1 $2 | tail -1
+  echo -n "$(basename $so): "; AVD_LIB=$PWD/$so python scripts/prof_k2.py $1 $2 | head -2 | tr "\n" " "; echo
 done
