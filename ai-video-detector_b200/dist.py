@@ -74,3 +74,25 @@ def shard_clips(n_clips: int, rank: int, world: int):
     """Clip-sharding for batches of independent clips: the clip indices this rank analyses."""
     lo, hi = shard_bounds(n_clips, world)[rank]
     return range(lo, hi)
+
+
+def bind_to_gpu_numa(local_rank: int) -> bool:
+    """Pin the calling process to the CPUs NVML reports as closest to GPU `local_rank`, so that the pinned staging
+    buffers it allocates next land on that GPU's NUMA node (first touch).  On a two-socket 8-GPU host, eight ranks
+    whose staging memory sits on one socket share that socket's memory controllers and inter-socket link.
+    Returns False (and changes nothing) if NVML is unavailable."""
+    try:
+        import os
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(local_rank)
+        n = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, n)
+        cpus = {64 * i + b for i, m in enumerate(mask) for b in range(64) if (m >> b) & 1}
+        cpus &= set(os.sched_getaffinity(0))
+        if not cpus:
+            return False
+        os.sched_setaffinity(0, cpus)
+        return True
+    except Exception:
+        return False

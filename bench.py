@@ -161,6 +161,10 @@ def main():
         return run_reference(args, rank, world)
     assert args.warmup >= 3 or os.environ.get("AVD_BENCH_ALLOW_SHORT"), "timing rules: at least 3 warm-up steps"
 
+    numa_bound = False
+    if world > 1 and os.environ.get("AVD_BIND_NUMA", "1") != "0":
+        from avd_b200 import dist as avd_dist     # staging memory on the GPU's own NUMA node (first touch after binding)
+        numa_bound = avd_dist.bind_to_gpu_numa(local_rank)
     # ---- synthetic input (host, before CUDA is touched so the CPU baseline may fork) ---------------------
     host_frames = np.empty((SAMPLES, H, W, 3), np.uint8)
     halo_np = np.empty((H, W, 3), np.uint8) if rank > 0 else None
@@ -294,7 +298,7 @@ def main():
             "scaling": "weak", "vs_baseline": None, "dtype": "u8 (K1 integer path) / f32+f64 (Farneback)", "data": "synthetic",
             "config": {"workload": "1080p 30fps 60s synthetic clip (1800 frames -> 120 sampled frames) per GPU: per-frame features + 119 flow pairs + timeline/fuse",
                        "frames_per_step_per_gpu": SAMPLES, "sharding": "none" if world == 1 else f"frame-chunk x{world}, 1-sample halo, all-gather of 160 B records",
-                       "l2_policy": "inputs (746 MB/GPU) larger than L2 (126 MB), no flush needed", "seed": SEED,
+                       "l2_policy": "inputs (746 MB/GPU) larger than L2 (126 MB), no flush needed", "seed": SEED, "numa_bound": numa_bound,
                        "device_path": "CUDA graph replay of the step's kernel launches" if use_graph else "plain stream launches"},
             "clocks": clocks, "gpu_launches": int(launches),
             "e2e": {"value": n_total * args.steps / dt_e2e, "unit": "frames/s", "h2d_bytes_per_step": int(FRAME_BYTES * (SAMPLES * world + world - 1)),
