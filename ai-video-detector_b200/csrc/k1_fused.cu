@@ -164,6 +164,7 @@ struct Band {
     uint32_t sbase;                       // shared address of the header
     uint32_t stage;                       // shared address of stage 0
     uint32_t slot;                        // shared address of this thread's private gray slot
+    uint32_t sp0, rb1, rb2;               // this thread's strip in stage 0; one and two rows in bytes
     int row_bytes, nseq;
     int H, own0;
     const uint8_t *frame;
@@ -275,27 +276,27 @@ __device__ __forceinline__ void lap_step(const Band &B, const RowSet &U, const R
 }
 
 // sequence row q of the band = source row own0-1+q, reflected at the frame edges (BORDER_REFLECT_101)
-__device__ __forceinline__ void issue_row(const Band &B, int q, int s)
+__device__ __forceinline__ void issue_row(const Band &B, int q, uint32_t stage_off, uint32_t bar_off)
 {
     int r = B.own0 - 1 + q;
     r = r < 0 ? 1 : (r >= B.H ? B.H - 2 : r);
-    const uint32_t bar = B.sbase + OFF_FULL + 8 * s;   // s = 3 * group + position
+    const uint32_t bar = B.sbase + OFF_FULL + bar_off;
     mbar_expect_tx(bar, (uint32_t)B.row_bytes);
     // the two first and two last rows of a band are also read by the neighbouring bands: do not mark them evict-first
     const bool shared_row = q < 2 || q >= B.nseq - 2;
-    tma_load_1d(B.stage + s * B.row_bytes, B.frame + (size_t)r * B.pitch, (uint32_t)B.row_bytes, bar, shared_row ? B.pol_keep : B.pol_stream);
+    tma_load_1d(B.stage + stage_off, B.frame + (size_t)r * B.pitch, (uint32_t)B.row_bytes, bar, shared_row ? B.pol_keep : B.pol_stream);
 }
 
 // Stage s holds sequence row q: convert this thread's strip to gray (row set R); on tap rows of the thumbnail also
 // advance this thread's thumbnail columns.  Returns 1 in lane 0 of the warp that was last to leave the stage
 // (passed on to release_finish).
 template <int POS, int JT, int TM>
-__device__ __forceinline__ uint32_t load_row(const Band &B, int q, int grp, uint32_t parity, uint32_t &ok, uint32_t nbar, uint32_t npar,
+__device__ __forceinline__ uint32_t load_row(const Band &B, int q, uint32_t goff, uint32_t gbar, uint32_t parity, uint32_t &ok, uint32_t nbar, uint32_t npar,
                                              int tid, bool first, bool last, RowSet &R, Thumb<JT> &T)
 {
-    const int S = 3 * grp + POS;
-    if (!ok) mbar_wait_slow(B.sbase + OFF_FULL + 8 * S, parity);
-    const uint32_t sp = B.stage + S * B.row_bytes + 48 * tid;
+    // goff / gbar: byte offsets of the stage group (0 or 3 rows; 0 or 3 barriers), toggled by the caller: no per-row multiplies
+    if (!ok) mbar_wait_slow(B.sbase + OFF_FULL + 8 * POS + gbar, parity);
+    const uint32_t sp = B.sp0 + goff + (POS == 0 ? 0u : (POS == 1 ? B.rb1 : B.rb2));
     uint4 q0, q1, q2;
     uint32_t wl, wr;
     asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(q0.x), "=r"(q0.y), "=r"(q0.z), "=r"(q0.w) : "r"(sp));
@@ -314,7 +315,7 @@ __device__ __forceinline__ uint32_t load_row(const Band &B, int q, int grp, uint
     uint32_t aR = __dp2a_hi(K.r0, wr, __dp2a_lo(K.bg, wr, K.rnd));
     // every lane of this warp has its bytes in registers: count the warp off the stage (result used much later)
     __syncwarp();
-    const uint32_t ticket = stage_arrive(B.sbase + OFF_CNT + 8 * S, (tid & 31) == 0 ? 1u : 0u, aL ^ aR);
+    const uint32_t ticket = stage_arrive(B.sbase + OFF_CNT + 8 * POS + gbar, (tid & 31) == 0 ? 1u : 0u, aL ^ aR);
     ok = mbar_try(nbar, npar);               // next row's stage: checked at the top of the next step
     aL = first ? a[1] : aL;
     aR = last ? a[14] : aR;
@@ -362,9 +363,9 @@ __device__ __forceinline__ uint32_t load_row(const Band &B, int q, int grp, uint
 
 // the warp that arrived last at stage S refills it with sequence row q + NRS
 template <int POS>
-__device__ __forceinline__ void release_finish(const Band &B, int q, int grp, uint32_t ticket)
+__device__ __forceinline__ void release_finish(const Band &B, int q, uint32_t goff, uint32_t gbar, uint32_t ticket)
 {
-    if (ticket == 1u && q + NRS < B.nseq) issue_row(B, q + NRS, 3 * grp + POS);
+    if (ticket == 1u && q + NRS < B.nseq) issue_row(B, q + NRS, goff + POS * B.row_bytes, gbar + 8 * POS);
 }
 
 __device__ __forceinline__ uint8_t sat_rne(float v)
@@ -400,6 +401,7 @@ __global__ void __launch_bounds__(MAXT, MINB) k1_fused_kernel(K1Params P)
     Band B;
     B.sbase = sbase; B.stage = sbase + HDR; B.slot = sbase + HDR + NRS * P.row_bytes + 64 + SLOT * tid;
     B.row_bytes = P.row_bytes; B.nseq = nseq;
+    B.sp0 = sbase + HDR + 48 * tid; B.rb1 = (uint32_t)P.row_bytes; B.rb2 = 2u * (uint32_t)P.row_bytes;
     B.K.load();
     B.todd = tab->lx[0].i0 & 1;
     B.H = H; B.own0 = own0; B.frame = frame; B.pitch = P.pitch;
@@ -413,7 +415,7 @@ __global__ void __launch_bounds__(MAXT, MINB) k1_fused_kernel(K1Params P)
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        for (int q = 0; q < NRS; q++) issue_row(B, q, q);
+        for (int q = 0; q < NRS; q++) issue_row(B, q, q * P.row_bytes, 8 * q);
     }
     if (tid < 32) ((int *)(smem + OFF_CELL))[tid] = 0;
     if (tid == 32) ((uint32_t *)(smem + OFF_MISC))[1] = 0;          // warps that finished the band
@@ -458,14 +460,15 @@ __global__ void __launch_bounds__(MAXT, MINB) k1_fused_kernel(K1Params P)
     const int wh = 32 * own0 - b * H;                     // weight of the head row (sequence row 0), 1/32 units
     const int wt = (b + 1) * H - 32 * (own1 - 1);         // weight of the last owned row, 1/32 units (32 = full)
 
-    auto full_bar = [&](int st) { return sbase + OFF_FULL + 8 * st; };
-    uint32_t par = 0;
-    int grp = 0;
-    uint32_t ok = mbar_try(full_bar(0), 0u);
-    uint32_t t0 = load_row<0, JT, TM>(B, 0, 0, 0u, ok, full_bar(1), 0u, tid, first, last, R0, T);
-    release_finish<0>(B, 0, 0, t0);
-    uint32_t t1 = load_row<1, JT, TM>(B, 1, 0, 0u, ok, full_bar(2), 0u, tid, first, last, R1, T);
-    release_finish<1>(B, 1, 0, t1);
+    // stage group state: byte offset of the group's first stage / first barrier (toggled, never multiplied), phase parity
+    const uint32_t g3 = NGRP > 1 ? 3u * (uint32_t)P.row_bytes : 0u, gb3 = NGRP > 1 ? 24u : 0u;
+    const uint32_t fbar = sbase + OFF_FULL;
+    uint32_t par = 0, goff = 0, gbar = 0;
+    uint32_t ok = mbar_try(fbar, 0u);
+    uint32_t t0 = load_row<0, JT, TM>(B, 0, 0u, 0u, 0u, ok, fbar + 8, 0u, tid, first, last, R0, T);
+    release_finish<0>(B, 0, 0u, 0u, t0);
+    uint32_t t1 = load_row<1, JT, TM>(B, 1, 0u, 0u, 0u, ok, fbar + 16, 0u, tid, first, last, R1, T);
+    release_finish<1>(B, 1, 0u, 0u, t1);
     int tv = (int)row_sum(R0) - (int)row_sum(R1);         // vertical part of sum L telescopes to 4 rows per band
     int mcA = 0, mcB = 0;                                  // cell sums in 1/32 units
     if (wh > 0) {
@@ -505,21 +508,22 @@ __global__ void __launch_bounds__(MAXT, MINB) k1_fused_kernel(K1Params P)
 
     int q = 2;
     while (true) {
-        const int ng = grp + 1 == NGRP ? 0 : grp + 1;
-        const uint32_t np = grp + 1 == NGRP ? par ^ 1u : par;
-        uint32_t tk = load_row<2, JT, TM>(B, q, grp, par, ok, full_bar(3 * ng), np, tid, first, last, R2, T);
+        // the group after this one: the other group (NRS = 6) or the same one (NRS = 3); the parity flips when group 0 comes round again
+        const uint32_t ngoff = goff ^ g3, ngbar = gbar ^ gb3;
+        const uint32_t np = ngbar == 0 ? par ^ 1u : par;
+        uint32_t tk = load_row<2, JT, TM>(B, q, goff, gbar, par, ok, fbar + ngbar, np, tid, first, last, R2, T);
         lap_step<JT, TM>(B, R0, R1, R2, A, T, row_info(q - 1));
-        release_finish<2>(B, q, grp, tk);
+        release_finish<2>(B, q, goff, gbar, tk);
         if (q == nseq - 1) { band_end(R1, R2); break; }
-        q++; grp = ng; par = np;
-        tk = load_row<0, JT, TM>(B, q, grp, par, ok, full_bar(3 * grp + 1), par, tid, first, last, R0, T);
+        q++; goff = ngoff; gbar = ngbar; par = np;
+        tk = load_row<0, JT, TM>(B, q, goff, gbar, par, ok, fbar + gbar + 8, par, tid, first, last, R0, T);
         lap_step<JT, TM>(B, R1, R2, R0, A, T, row_info(q - 1));
-        release_finish<0>(B, q, grp, tk);
+        release_finish<0>(B, q, goff, gbar, tk);
         if (q == nseq - 1) { band_end(R2, R0); break; }
         q++;
-        tk = load_row<1, JT, TM>(B, q, grp, par, ok, full_bar(3 * grp + 2), par, tid, first, last, R1, T);
+        tk = load_row<1, JT, TM>(B, q, goff, gbar, par, ok, fbar + gbar + 16, par, tid, first, last, R1, T);
         lap_step<JT, TM>(B, R2, R0, R1, A, T, row_info(q - 1));
-        release_finish<1>(B, q, grp, tk);
+        release_finish<1>(B, q, goff, gbar, tk);
         if (q == nseq - 1) { band_end(R0, R1); break; }
         q++;
     }
