@@ -200,7 +200,7 @@ void avd_destroy(avd_ctx *ctx)
     cudaDeviceSynchronize();
     for (auto &kv : ctx->tables) cudaFree(kv.second);
     cudaFree(ctx->gray); cudaFree(ctx->area_rows); cudaFree(ctx->k2_ws); cudaFree(ctx->ring);
-    cudaFree(ctx->thumbs); cudaFree(ctx->recs); cudaFree(ctx->area32); cudaFree(ctx->fixlist);
+    cudaFree(ctx->thumbs); cudaFree(ctx->recs); cudaFree(ctx->area32); cudaFree(ctx->fixlist); cudaFree(ctx->k3_ws);
     for (int i = 0; i < 4; i++) { cudaEventDestroy(ctx->ev_copied[i]); cudaEventDestroy(ctx->ev_free[i]); }
     cudaStreamDestroy(ctx->compute); cudaStreamDestroy(ctx->copy);
     cudaGetLastError();
@@ -382,7 +382,8 @@ int avd_analyze_host(avd_ctx *ctx, const uint8_t *const *h_frames, int n, int H,
     int rc = check_shape(ctx, n, H, W, row_pitch);
     if (rc) return rc;
     if (n == 0) return AVD_OK;
-    if (!h_frames || !h_rec) { ctx->err = "null buffer"; return AVD_ERR_ARG; }
+    if (!h_frames) { ctx->err = "null buffer"; return AVD_ERR_ARG; }
+    ctx->recs_n = 0;
     AVD_CUDA(ctx, cudaSetDevice(ctx->device));
     // device frame layout inside a slot: dense rows padded to 16 bytes so the fused kernel applies
     size_t dpitch = ((size_t)W * 3 + 15) & ~(size_t)15;
@@ -429,8 +430,9 @@ int avd_analyze_host(avd_ctx *ctx, const uint8_t *const *h_frames, int n, int H,
         AVD_CUDA(ctx, cudaEventRecord(ctx->ev_free[slot], ctx->compute));
         if ((rc = avd_flow_stats(ctx, th, nb, f0 > 0 ? th - (size_t)AVD_T * AVD_T : nullptr, rec, ctx->compute))) return rc;
     }
-    AVD_CUDA(ctx, cudaMemcpyAsync(h_rec, ctx->recs, (size_t)n * sizeof(avd_sample_rec), cudaMemcpyDeviceToHost, ctx->compute));
+    if (h_rec) AVD_CUDA(ctx, cudaMemcpyAsync(h_rec, ctx->recs, (size_t)n * sizeof(avd_sample_rec), cudaMemcpyDeviceToHost, ctx->compute));
     AVD_CUDA(ctx, cudaStreamSynchronize(ctx->compute));
+    ctx->recs_n = n;
     return AVD_OK;
 }
 

@@ -170,11 +170,12 @@ class Engine:
         return rec.cpu().numpy().view(REC_DTYPE).reshape(-1)
 
     # -- host path (the public, torch-free call) --------------------------------------------------------
-    def analyze_host(self, frames) -> np.ndarray:
+    def analyze_host(self, frames, keep_on_device: bool = False):
         """frames: sequence of (H,W,3) uint8 arrays (same shape, rows contiguous) or one (n,H,W,3) array,
-        ideally in pinned memory (`Engine.pinned`).  Streams them through K1/K2 and returns records."""
+        ideally in pinned memory (`Engine.pinned`).  Streams them through K1/K2 and returns records.
+        keep_on_device: leave the records in HBM for `scoring.score_jobs` (K3) and return None."""
         n = len(frames)
-        out = np.zeros(n, REC_DTYPE)
+        out = None if keep_on_device else np.zeros(n, REC_DTYPE)
         if n == 0:
             return out
         f0 = frames[0]
@@ -187,7 +188,8 @@ class Engine:
                 raise AvdError("analyze_host: frames must be uint8 (H,W,3), packed BGR, one common shape and row pitch")
             ptrs[i] = f.ctypes.data
         with self._lock:
-            self._check(self.L.avd_analyze_host(self.h, ptrs, n, H, W, pitch, C.c_void_p(out.ctypes.data)), "avd_analyze_host")
+            self._check(self.L.avd_analyze_host(self.h, ptrs, n, H, W, pitch,
+                                                C.c_void_p(out.ctypes.data) if out is not None else None), "avd_analyze_host")
         return out
 
 

@@ -66,6 +66,28 @@ def _real_bonus(flow_mean, texture_var, sc_rate, dup_density) -> float:
     return b
 
 
+def reason_for(label: str, dup_density: float, tts_like: float, hints: dict) -> str:
+    """The explanation string of a label (fusion.py:82-100)."""
+    comp = hints.get("compression", "normal")
+    if label == "real":
+        why = []
+        if dup_density > 0.25:
+            why.append("molti frame duplicati")
+        if comp in ("heavy", "very_heavy"):
+            why.append("compressione pesante")
+        return "; ".join(why or ["segnali audio/video coerenti con ripresa reale"])
+    if label == "ai":
+        why = []
+        if tts_like > 0.6:
+            why.append("audio TTS-like elevato")
+        if dup_density > 0.2:
+            why.append("molti frame duplicati")
+        if hints.get("video_has_signal", True) is False:
+            why.append("segnali video deboli")
+        return "; ".join(why or ["pattern e indizi coerenti con generazione AI"])
+    return "segnali misti o neutri"
+
+
 def fuse(audio: dict, video: dict, hints: dict, thresholds: Thresholds = THRESHOLDS, with_raw: bool = False) -> dict:
     a_t = audio.get("timeline") or []
     v_t = video.get("timeline") or video.get("timeline_ai") or []
@@ -97,25 +119,8 @@ def fuse(audio: dict, video: dict, hints: dict, thresholds: Thresholds = THRESHO
     disagree = float(abs(np.mean(a) - np.mean(v)))
     conf = float(np.clip(0.20 + 2.2 * spread - pen - 0.5 * max(0.0, 0.3 - disagree), 0.10, 0.99))
 
-    comp = hints.get("compression", "normal")
-    if score <= thresholds.real_max:
-        label, why = "real", []
-        if dup_density > 0.25:
-            why.append("molti frame duplicati")
-        if comp in ("heavy", "very_heavy"):
-            why.append("compressione pesante")
-        reason = "; ".join(why or ["segnali audio/video coerenti con ripresa reale"])
-    elif score >= thresholds.ai_min:
-        label, why = "ai", []
-        if tts_like > 0.6:
-            why.append("audio TTS-like elevato")
-        if dup_density > 0.2:
-            why.append("molti frame duplicati")
-        if hints.get("video_has_signal", True) is False:
-            why.append("segnali video deboli")
-        reason = "; ".join(why or ["pattern e indizi coerenti con generazione AI"])
-    else:
-        label, reason = "uncertain", "segnali misti o neutri"
+    label = "real" if score <= thresholds.real_max else ("ai" if score >= thresholds.ai_min else "uncertain")
+    reason = reason_for(label, dup_density, tts_like, hints)
 
     out = {"result": {"label": label, "ai_score": round(score, 2), "confidence": round(conf, 2), "reason": reason},
            "timeline_binned": bin_timeline(tl.tolist()), "peaks": peaks}

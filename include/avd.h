@@ -105,10 +105,56 @@ int avd_gray(avd_ctx *ctx, const uint8_t *d_bgr, int H, int W, size_t row_pitch,
  * streamed to the device in chunks on a copy stream while K1/K2 run on the compute stream; records come
  * back to h_rec[0..n).  For a chunk of a longer clip (multi-GPU frame-chunk sharding, or host-side
  * streaming of a long clip) the caller passes the sample *before* the chunk as frame 0 (one-sample halo)
- * and drops h_rec[0].  Synchronous: returns when h_rec is complete.
+ * and drops h_rec[0].  Synchronous: returns when h_rec is complete.  h_rec = NULL leaves the records on the device
+ * (for avd_score_clips).
  */
 int avd_analyze_host(avd_ctx *ctx, const uint8_t *const *h_frames, int n, int H, int W, size_t row_pitch,
                      avd_sample_rec *h_rec);
+
+/*
+ * K3 -- the per-clip scoring tail on the device, for batches of clips whose records are already in HBM (SURVEY.md
+ * section 8(f)-3).  One call scores n_clips clips; nothing but the compact scores and timelines crosses PCIe.  Replaces
+ *   ai_susp per sample, dup_density, scene_change_rate, flow_mean, flow_var, texture_var, timeline pad/truncate   video.py:54-81
+ *   fuse: weights, agreement, bonuses, fused timeline, peaks, score, spread, confidence, label, 3-tap binning,
+ *         round(score, 2), round(conf, 2)                                                                       fusion.py:7-14,16-109
+ * in float64 with NumPy's operation order (pairwise sums of np.mean / np.var / np.std, the two-pass variance, the
+ * accumulation order of np.convolve(..., "same")), so results are equal to the reference's, not merely close.
+ * What stays with the caller because it is string work: hints -> `pen` (fusion.py:37-41) and label/conditions -> `reason`.
+ *
+ * A job names the clip's records (the first is treated as having no predecessor, video.py:20,26), its timeline
+ * length tlen = int(max(1, round(duration))) (Python round, video.py:73) and -- if do_fuse -- the audio side:
+ * audio timeline = h_tl_in[audio_off .. audio_off+audio_len), flags speech_ratio / tts_like, penalty `pen`.
+ * video_given = 1 scores a video timeline and summary supplied by the caller instead of records (any dict fuse()
+ * accepts).  Outputs per clip start at out_off and are L = max(audio_len, video timeline length, 1) long (tlen when
+ * do_fuse = 0): h_vtimeline = the video timeline as fuse leaves it (padded in place, fusion.py:20-21; its first
+ * score.vlen entries are video.analyze's timeline), h_fused = the clipped fused timeline, h_binned, h_peaks (1 = peak).
+ * d_rec = NULL scores the records of the last avd_analyze_host run on this context (which may be given h_rec = NULL
+ * to keep the records on the device).  Synchronous on `stream`.
+ */
+typedef struct avd_clip_job {
+    int32_t rec_first, rec_count;      /* records of the clip inside d_rec, sample order (count >= 0) */
+    int32_t npix;                      /* H*W of its frames */
+    int32_t tlen;                      /* >= 1 */
+    int32_t do_fuse;
+    int32_t audio_off, audio_len;
+    int32_t video_given, vgiven_off, vgiven_len;
+    int32_t out_off, pad_;
+    double  speech_ratio, tts_like, pen;
+    double  thresh_real_max, thresh_ai_min;                        /* fusion.py:4-5 */
+    double  g_flow_mean, g_texture_var, g_sc_rate, g_dup_density;  /* video_given: the summary fields fuse reads */
+} avd_clip_job;
+
+typedef struct avd_clip_score {
+    double  dup_density, scene_change_rate, flow_mean, flow_var, texture_var;   /* video.py:64-69 */
+    double  score, spread, conf;         /* before rounding */
+    double  ai_score, confidence;        /* round(score, 2), round(conf, 2)   fusion.py:103-104 */
+    int32_t label;                       /* 0 real, 1 uncertain, 2 ai          fusion.py:82-100 */
+    int32_t vlen, L, n_peaks;
+} avd_clip_score;
+
+int avd_score_clips(avd_ctx *ctx, const avd_sample_rec *d_rec, int n_rec, const avd_clip_job *h_jobs, int n_clips,
+                    const double *h_tl_in, int n_tl_in, avd_clip_score *h_scores, double *h_vtimeline,
+                    double *h_fused, double *h_binned, uint8_t *h_peaks, int n_out, void *stream);
 
 /* Counters for bench.py: number of kernel launches issued by this context since creation. */
 uint64_t avd_launch_count(const avd_ctx *ctx);

@@ -8,7 +8,7 @@ import os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
 import avd_b200.synth as synth
-from avd_b200 import dist as avd_dist, video
+from avd_b200 import dist as avd_dist, fusion, hints as avd_hints, scoring, video
 from avd_b200.engine import Engine
 
 rows = []
@@ -72,6 +72,20 @@ one = video.analyze_frames(clips[7], metas[7], engine=eng)
 same = outs[7] == one
 rows.append(("[3] 256 x 720p 5s clips, clip-sharded x8: one rank's 32 clips (320 samples)", f"{1e3*dt_b:.1f} ms = {320/dt_b:.0f} frames/s per GPU",
              "-", "batched result of a clip == that clip analysed alone: %s" % same))
+assert same
+
+# the same 32 clips through to fused verdicts: host tail (records -> NumPy tail -> fuse per clip) against K3 (records stay in HBM)
+hn = [avd_hints.compute_hints(m) for m in metas]
+def host_tail():
+    vs = video.analyze_frames_batch(clips, metas, engine=eng)
+    return [{"video": v, "fusion": fusion.fuse(fusion.neutral_audio(5), v, h)} for v, h in zip(vs, hn)]
+def device_tail():
+    return scoring.score_clip_batch(eng, clips, metas, audios=[fusion.neutral_audio(5) for _ in clips], hints=hn)
+dt_h, out_h = timed(host_tail, reps=3)
+dt_d, out_d = timed(device_tail, reps=3)
+same = out_h == out_d
+rows.append(("[3] same 32 clips, frames -> fused verdicts", f"host tail {1e3*dt_h:.1f} ms = {320/dt_h:.0f} frames/s; device tail (K3) {1e3*dt_d:.1f} ms = {320/dt_d:.0f} frames/s",
+             "-", "device tail == host tail (every float equal): %s" % same))
 assert same
 
 print("| config | avd-b200 (host frames -> results, one B200) | one rank's share | check |")

@@ -269,3 +269,43 @@ def test_shape_plan_kernel_choice():
     for (H, W), k in want.items():
         assert _plan(H, W).k1_path == k, (H, W)
     assert _plan(960, 1280).area_int == 1 and _plan(1080, 1920).area_int == 0 and _plan(640, 640).thumb_2x2 == 1
+
+
+def test_scoring_job_layout_matches_header(tmp_path):
+    """The NumPy dtypes scoring.py packs jobs / reads scores with are the C structs of include/avd.h."""
+    from avd_b200 import scoring
+    src = tmp_path / "lay.c"
+    fields_j = [n for n in scoring.JOB_DTYPE.names]
+    fields_s = [n for n in scoring.SCORE_DTYPE.names]
+    body = "".join(f'printf("j %s %zu\\n", "{f}", offsetof(avd_clip_job, {f}));' for f in fields_j)
+    body += "".join(f'printf("s %s %zu\\n", "{f}", offsetof(avd_clip_score, {f}));' for f in fields_s)
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "avd.h"\nint main(){' + body +
+                   'printf("J %zu\\nS %zu\\n", sizeof(avd_clip_job), sizeof(avd_clip_score));return 0;}')
+    exe = tmp_path / "lay"
+    subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
+    out = subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split("\n")
+    for line in out:
+        t = line.split()
+        if not t:
+            continue
+        if t[0] == "j":
+            assert scoring.JOB_DTYPE.fields[t[1]][1] == int(t[2]), line
+        elif t[0] == "s":
+            assert scoring.SCORE_DTYPE.fields[t[1]][1] == int(t[2]), line
+        elif t[0] == "J":
+            assert scoring.JOB_DTYPE.itemsize == int(t[1])
+        elif t[0] == "S":
+            assert scoring.SCORE_DTYPE.itemsize == int(t[1])
+
+
+def test_scoring_joblist_offsets_and_timeline_length():
+    from avd_b200 import scoring
+    assert [scoring.timeline_length(d) for d in (0.0, 0.4, 0.5, 1.5, 2.5, 3.5, 59.6)] == [1, 1, 1, 2, 2, 4, 60]   # half to even
+    jl = scoring.JobList()
+    jl.add(rec_first=0, rec_count=10, npix=64, tlen=5)                                                    # video only: 5 outputs
+    jl.add(rec_first=10, rec_count=3, npix=64, tlen=2, audio={"timeline": [0.1] * 7, "flags_audio": {}}, hints={"bpp": 0.5})
+    jl.add(video={"timeline": [], "summary": {}}, audio={"timeline": []}, hints={})                       # both empty: L = 1
+    jobs, tl_in, n_out = jl.arrays()
+    assert jobs["out_off"].tolist() == [0, 5, 12] and n_out == 13 and len(tl_in) == 7
+    assert jobs["do_fuse"].tolist() == [0, 1, 1] and jobs["video_given"].tolist() == [0, 0, 1]
+    assert float(jobs["pen"][1]) == 0.0 and float(jobs["pen"][2]) == 0.05                                 # bpp default 0.0 < 0.07
