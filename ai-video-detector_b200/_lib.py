@@ -19,7 +19,7 @@ REC_HAS_PREV, REC_HAS_FLOW = 1, 2
 SYMBOLS = ["avd_version", "avd_device_count", "avd_create", "avd_destroy", "avd_last_error", "avd_sync",
            "avd_host_alloc", "avd_host_free", "avd_frames_features", "avd_flow_stats", "avd_flow_fields",
            "avd_gray", "avd_analyze_host", "avd_launch_count", "avd_set_k1_mode", "avd_profile_enable",
-           "avd_profile_read", "avd_shape_plan", "avd_score_clips"]
+           "avd_profile_read", "avd_shape_plan", "avd_score_clips", "avd_audio_windows"]
 
 
 class AvdError(RuntimeError):
@@ -59,5 +59,6 @@ def load():
     L.avd_profile_read.argtypes = [vp, C.c_char_p, sz]; L.avd_profile_read.restype = C.c_int
     L.avd_score_clips.argtypes = [vp, vp, C.c_int, vp, C.c_int, vp, C.c_int, vp, vp, vp, vp, vp, C.c_int, vp]
     L.avd_score_clips.restype = C.c_int
+    L.avd_audio_windows.argtypes = [vp, vp, C.c_longlong, C.c_int, vp, vp]; L.avd_audio_windows.restype = C.c_int
     _lib = L
     return L

@@ -200,7 +200,7 @@ void avd_destroy(avd_ctx *ctx)
     cudaDeviceSynchronize();
     for (auto &kv : ctx->tables) cudaFree(kv.second);
     cudaFree(ctx->gray); cudaFree(ctx->area_rows); cudaFree(ctx->k2_ws); cudaFree(ctx->ring);
-    cudaFree(ctx->thumbs); cudaFree(ctx->recs); cudaFree(ctx->area32); cudaFree(ctx->fixlist); cudaFree(ctx->k3_ws);
+    cudaFree(ctx->thumbs); cudaFree(ctx->recs); cudaFree(ctx->area32); cudaFree(ctx->fixlist); cudaFree(ctx->k3_ws); cudaFree(ctx->k4_ws);
     for (int i = 0; i < 4; i++) { cudaEventDestroy(ctx->ev_copied[i]); cudaEventDestroy(ctx->ev_free[i]); }
     cudaStreamDestroy(ctx->compute); cudaStreamDestroy(ctx->copy);
     cudaGetLastError();

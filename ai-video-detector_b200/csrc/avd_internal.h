@@ -65,6 +65,7 @@ struct avd_ctx {
     uint8_t *thumbs = nullptr; size_t thumbs_cap = 0;
     avd_sample_rec *recs = nullptr; size_t recs_cap = 0; int recs_n = 0;   // recs_n: records of the last host run
     void *k3_ws = nullptr; size_t k3_ws_cap = 0;               // avd_score_clips workspace
+    void *k4_ws = nullptr; size_t k4_ws_cap = 0;               // avd_audio_windows workspace
     uint8_t *area32 = nullptr; size_t area32_cap = 0;
     uint32_t *fixlist = nullptr; size_t fixlist_cap = 0;   // streaming K1: [0] = count, then uncertified cells
     // optional per-kernel timing (avd_profile_enable): CUDA events around every launch, on its stream

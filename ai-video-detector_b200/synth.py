@@ -112,3 +112,43 @@ def noise_frames(n: int, H: int, W: int, seed: int) -> np.ndarray:
     """Worst case for the per-frame kernel: i.i.d. uniform bytes (max Laplacian energy, incompressible)."""
     rng = np.random.default_rng([seed, 99, H, W])
     return rng.integers(0, 256, (n, H, W, 3), dtype=np.uint8)
+
+
+def audio(seed: int, n_samples: int, kind: str = "speech") -> np.ndarray:
+    """Mono 16 kHz test audio as float32 in [-1, 1) (what soundfile hands audio.py:15 of the reference), built from
+    int16 PCM with integer arithmetic only, so every machine regenerates the same samples.
+
+    kinds: "noise" white noise; "speech" noise bursts of varying level separated by exact silence (voiced / unvoiced /
+    pause pattern, 0.2-0.9 s segments); "tone" a 125-sample triangle wave with a little noise; "silence" zeros;
+    "quiet" noise of +-2 LSB.
+    """
+    rng = np.random.default_rng([seed, 411])
+    n = int(n_samples)
+    if kind == "silence":
+        pcm = np.zeros(n, np.int32)
+    elif kind == "noise":
+        pcm = rng.integers(-12000, 12001, n, dtype=np.int32)
+    elif kind == "quiet":
+        pcm = rng.integers(-2, 3, n, dtype=np.int32)
+    elif kind == "tone":
+        t = np.arange(n, dtype=np.int32) % 125
+        tri = np.where(t < 63, t * 300, (125 - t) * 300) - 9300
+        pcm = tri + rng.integers(-40, 41, n, dtype=np.int32)
+    elif kind == "speech":
+        pcm = np.zeros(n, np.int32)
+        pos, state = 0, 0
+        while pos < n:
+            seg = int(rng.integers(3200, 14401))
+            end = min(n, pos + seg)
+            if state % 3 == 0:      # voiced: low-passed noise (running mean of 8) at a random level
+                amp = int(rng.integers(4000, 16001))
+                x = rng.integers(-amp, amp + 1, end - pos + 8, dtype=np.int32)
+                c = np.cumsum(x, dtype=np.int64)
+                pcm[pos:end] = ((c[8:] - c[:-8]) // 4).astype(np.int32)[:end - pos]
+            elif state % 3 == 1:    # unvoiced: white noise
+                amp = int(rng.integers(500, 3001))
+                pcm[pos:end] = rng.integers(-amp, amp + 1, end - pos, dtype=np.int32)
+            pos, state = end, state + 1
+    else:
+        raise ValueError(kind)
+    return (np.clip(pcm, -32768, 32767).astype(np.float32) / np.float32(32768.0)).astype(np.float32)

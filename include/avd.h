@@ -156,6 +156,21 @@ int avd_score_clips(avd_ctx *ctx, const avd_sample_rec *d_rec, int n_rec, const 
                     const double *h_tl_in, int n_tl_in, avd_clip_score *h_scores, double *h_vtimeline,
                     double *h_fused, double *h_binned, uint8_t *h_peaks, int n_out, void *stream);
 
+/*
+ * K4 -- per-window features of the audio analyzer.  h_wav: the mono float32 samples the
+ * reference's decode helper returns (audio.py:7-20, 16 kHz); win = max(1, int(sr * 0.5)) samples (audio.py:38; at most
+ * 9000).  For every window w = 0 .. ceil(n_samples / win) - 1 (the last one ragged) writes five float64 values to
+ * h_feats[5 w ..]: what audio.py:43-60 appends to rms, zcr, flat, roll, sc_cent:
+ *   float(np.sqrt((seg**2).mean()))                      float32 arithmetic, exact
+ *   float(np.mean(np.abs(np.diff(np.sign(seg)))) / 2.0)  exact (NaN for a one-sample window, like the reference)
+ *   flatness  exp(mean(log(mag))) / mean(mag),  mag = |np.fft.rfft(seg * np.hanning(len))| + 1e-9
+ *   roll-off  first bin whose running sum reaches 0.85 * sum(mag), divided by the number of bins
+ *   centroid  sum(linspace(0, 1, bins) * mag) / sum(mag)
+ * The spectrum is a direct float64 DFT with correctly rounded twiddles (any window length, also prime).  The
+ * O(windows) tail (percentile, variances, tts_like, timeline; audio.py:63-111) is host arithmetic.  Synchronous.
+ */
+int avd_audio_windows(avd_ctx *ctx, const float *h_wav, long long n_samples, int win, double *h_feats, void *stream);
+
 /* Counters for bench.py: number of kernel launches issued by this context since creation. */
 uint64_t avd_launch_count(const avd_ctx *ctx);
 

@@ -309,3 +309,20 @@ def test_scoring_joblist_offsets_and_timeline_length():
     assert jobs["out_off"].tolist() == [0, 5, 12] and n_out == 13 and len(tl_in) == 7
     assert jobs["do_fuse"].tolist() == [0, 1, 1] and jobs["video_given"].tolist() == [0, 0, 1]
     assert float(jobs["pen"][1]) == 0.0 and float(jobs["pen"][2]) == 0.05                                 # bpp default 0.0 < 0.07
+
+
+def test_audio_tail_matches_reference(synth):
+    """audio.result_from_features (the host tail of the audio drop-in) on the oracle's per-window features == the
+    reference's dicts; and the failure result has the reference's shape (audio.py:112-118)."""
+    import json
+    from avd_b200 import audio
+    from oracle import audio_oracle
+    with open(os.path.join(ROOT, "tests", "golden", "golden_audio.json")) as f:
+        G = json.load(f)
+    for c in G["cases"]:
+        wav = synth.audio(c["seed"], c["n"], c["kind"])
+        with np.errstate(all="ignore"):
+            feats = np.stack(audio_oracle.window_features(wav, c["sr"]), axis=1)
+            assert audio.result_from_features(feats, len(wav), c["sr"]) == c["out"], c["name"]
+    bad = audio.analyze("/nonexistent/clip.mp4", {"duration": 2.6})
+    assert bad["scores"] == {} and "error" in bad["flags_audio"] and bad["timeline"] == [0.5, 0.5, 0.5]

@@ -111,3 +111,20 @@ def test_quirks(oracle):
     assert oracle.sample_step(0) == 15 and oracle.sample_step(1) == 1      # `fps or 30`; max(1, round(.5)=0)
     r = oracle.video_result([], 10, 10, 30.0, 2.5)                          # no samples: [0.5]*tlen, round(2.5)=2
     assert r["timeline"] == [0.5, 0.5] and r["summary"]["flow_mean"] == 0.0
+
+
+def test_audio_oracle_reproduces_reference_dicts(synth):
+    """oracle/audio_oracle.py against the dicts the reference's own audio.analyze returned (make_golden_audio.py)."""
+    import hashlib
+    import json
+    import os
+    from conftest import ROOT
+    from oracle import audio_oracle
+    with open(os.path.join(ROOT, "tests", "golden", "golden_audio.json")) as f:
+        G = json.load(f)
+    assert len(G["cases"]) == 10
+    for c in G["cases"]:
+        wav = synth.audio(c["seed"], c["n"], c["kind"])
+        assert wav.dtype == np.float32 and hashlib.sha256(wav.tobytes()).hexdigest() == c["input_sha"], c["name"]
+        with np.errstate(all="ignore"):
+            assert audio_oracle.analyze_samples(wav, c["sr"]) == c["out"], c["name"]
