@@ -74,8 +74,8 @@ def test_audio_edge_cases(eng):
     assert np.array_equal(got[:, 0], want[:, 0]) and np.array_equal(got[:, 3], want[:, 3])
     assert np.allclose(got[:, [2, 4]], want[:, [2, 4]], rtol=FEAT_RTOL, atol=0)
     # stereo input: first channel only (audio.py:34-35)
-    st = np.stack([wav, -wav], axis=1)
-    assert audio.analyze_samples(st, 16000, engine=eng)["timeline"] == audio.analyze_samples(wav, 16000, engine=eng)["timeline"]
+    st = np.stack([wav[:8000], -wav[:8000]], axis=1)
+    assert audio.analyze_samples(st, 16000, engine=eng) == audio.analyze_samples(wav[:8000], 16000, engine=eng)
     with pytest.raises(AvdError):
         audio.window_features(np.zeros(48000, np.float32), 48000, engine=eng)   # 24000-sample windows: beyond the kernel's table
 
