@@ -274,6 +274,11 @@ def main():
     clocks_dev = sampler.result()
     # same loop again with per-launch CUDA events on (kept out of `value`: the events add ~1 us per launch)
     _, _, kern, _ = timed(lambda: step_device(graph=False), args.steps, prof=True)
+    for _ in range(args.warmup):
+        step_host()
+    sampler = ClockSampler(local_rank); sampler.start()
+    dt_e2e, _, _, result_e2e = timed(step_host, args.steps)
+    clocks_e2e = sampler.result()
     # BASELINE configs[4] / SURVEY 8(d) quote the per-frame kernel at >= 256 frames per launch: the same kernel on 256 resident
     # frames, reported next to the 120-frame launch of the step (extra information, not the `roofline.frac` of the contract)
     k1_256 = None
@@ -292,11 +297,6 @@ def main():
                 ms = k["ms"] / k["launches"]
                 k1_256 = {"frames_per_launch": 256, "ms_per_launch": ms, "achieved": FRAME_BYTES * 256 / (ms * 1e-3) / 1e9}
             del big
-    for _ in range(args.warmup):
-        step_host()
-    sampler = ClockSampler(local_rank); sampler.start()
-    dt_e2e, _, _, result_e2e = timed(step_host, args.steps)
-    clocks_e2e = sampler.result()
     clocks = dict(clocks_dev, samples_e2e=clocks_e2e["samples"], sm_mhz_e2e=clocks_e2e["sm_mhz"],
                   reasons=sorted(set(clocks_dev["reasons"]) | set(clocks_e2e["reasons"])))
 
