@@ -394,7 +394,7 @@ __device__ __forceinline__ float4 edge_fix(float4 q, int xb, int s)
 }
 
 template <bool STATS>
-__global__ void __launch_bounds__(32 * BX_WARPS) box_solve_ring_kernel(const float *__restrict__ Mall, float *__restrict__ flow, int k, int BX_SEG,
+__global__ void __launch_bounds__(32 * BX_WARPS, STATS ? 4 : 0) box_solve_ring_kernel(const float *__restrict__ Mall, float *__restrict__ flow, int k, int BX_SEG,
                                                                       int n_pairs, double *__restrict__ task_stats, int p_base)
 {
     extern __shared__ float4 bx_ring[];
