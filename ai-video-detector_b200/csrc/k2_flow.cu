@@ -648,7 +648,10 @@ int k2_flow(avd_ctx *ctx, const uint8_t *d_prev, const uint8_t *d_next, size_t p
         // Measured on B200 (profiles/r01_k2_notes.md): OFF is faster -- box_solve has only 30 warps of work per pair,
         // so a 16-pair sub-batch leaves most SMs idle (box_solve 1.06 -> 4.1 ms, update_matrices 0.69 -> 0.84 ms).
         // rows per box_solve segment, per level (AVD_K2_SEG="s0,s1,s2,s3" overrides; multiples of 8)
-        static int seg_rows[4] = {64, 16, 8, 8};
+        // 56 / 24 rows at levels 0 / 1: with 119 pairs (BASELINE's 120-sample clip) the launch is 536 / 417 CTAs, one wave of the
+        // 592 resident CTAs; 64 rows left a quarter of the slots empty at level 0 and 16 rows made level 1 595 CTAs, i.e. two waves.
+        // Fixed per level (not chosen per batch) so that a pair's flow never depends on the batch it is computed in.
+        static int seg_rows[4] = {56, 24, 8, 8};
         static bool seg_init = false;
         if (!seg_init) {
             if (const char *e = getenv("AVD_K2_SEG")) sscanf(e, "%d,%d,%d,%d", &seg_rows[0], &seg_rows[1], &seg_rows[2], &seg_rows[3]);
