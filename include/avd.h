@@ -166,7 +166,8 @@ int avd_score_clips(avd_ctx *ctx, const avd_sample_rec *d_rec, int n_rec, const 
  *   flatness  exp(mean(log(mag))) / mean(mag),  mag = |np.fft.rfft(seg * np.hanning(len))| + 1e-9
  *   roll-off  first bin whose running sum reaches 0.85 * sum(mag), divided by the number of bins
  *   centroid  sum(linspace(0, 1, bins) * mag) / sum(mag)
- * The spectrum is a direct float64 DFT with correctly rounded twiddles (any window length, also prime).  The
+ * The spectrum is float64: a two-stage DFT for full windows whose length factors as N1 x N2 <= 128 x 128 (8000 = 80 x 100),
+ * a direct DFT for the ragged last window (any length, also prime); twiddles are correctly rounded.  The
  * O(windows) tail (percentile, variances, tts_like, timeline; audio.py:63-111) is host arithmetic.  Synchronous.
  */
 int avd_audio_windows(avd_ctx *ctx, const float *h_wav, long long n_samples, int win, double *h_feats, void *stream);
