@@ -201,26 +201,11 @@ __device__ __forceinline__ float up2_sample(const float *__restrict__ c, int cs,
     return (r0 * ay0 + r1 * fy) * 2.f;
 }
 
-template <int FLOWSRC>
-__global__ void __launch_bounds__(256) update_matrices_kernel(const float *__restrict__ Rall, const float *__restrict__ flow,
-                                                              const float *__restrict__ coarse, float *__restrict__ Mall,
-                                                              float *__restrict__ flow_store, int k, int pair_img_mode, int p_base)
+// The five entries of the update matrix of one pixel (the library's FarnebackUpdateMatrices) for the
+// displacement (dx, dy): bilinear warp of R1, border scaling.  
+__device__ __forceinline__ void um_pixel(const float *__restrict__ R0, const float *__restrict__ R1, int s, int x, int y, float dx, float dy, float *m)
 {
-    const int s = lvl_size(k);
-    int x = blockIdx.x * 32 + threadIdx.x, y = blockIdx.y * 8 + threadIdx.y, p = blockIdx.z + p_base;
-    if (x >= s || y >= s) return;
-    int ia = pair_img_mode == 2 ? 2 * p : p, ib = ia + 1;
-    size_t plane = (size_t)s * s, o = (size_t)y * s + x;
-    const float *R0 = Rall + (size_t)ia * PYR_PX * 5 + (size_t)lvl_off(k) * 5;
-    const float *R1 = Rall + (size_t)ib * PYR_PX * 5 + (size_t)lvl_off(k) * 5;
-    float dx = 0.f, dy = 0.f;
-    if (FLOWSRC == 1) {
-        dx = flow[(size_t)p * 2 * plane + o]; dy = flow[(size_t)p * 2 * plane + plane + o];
-    } else if (FLOWSRC == 2) {
-        int cs = s >> 1;
-        const float *cf = coarse + (size_t)p * 2 * cs * cs;
-        dx = up2_sample(cf, cs, x, y); dy = up2_sample(cf + (size_t)cs * cs, cs, x, y);
-    }
+    const size_t plane = (size_t)s * s, o = (size_t)y * s + x;
     float fx = (float)x + dx, fy = (float)y + dy;
     int x1 = (int)floorf(fx), y1 = (int)floorf(fy);
     fx -= (float)x1; fy -= (float)y1;
@@ -247,12 +232,37 @@ __global__ void __launch_bounds__(256) update_matrices_kernel(const float *__res
                    (y < B ? border[y] : 1.f) * (y >= s - B ? border[s - y - 1] : 1.f);
         r2 *= sc; r3 *= sc; r4 *= sc; r5 *= sc; r6 *= sc;
     }
+    m[0] = r4 * r4 + r6 * r6;
+    m[1] = (r4 + r5) * r6;
+    m[2] = r5 * r5 + r6 * r6;
+    m[3] = r4 * r2 + r6 * r3;
+    m[4] = r6 * r2 + r5 * r3;
+}
+
+template <int FLOWSRC>
+__global__ void __launch_bounds__(256) update_matrices_kernel(const float *__restrict__ Rall, const float *__restrict__ flow,
+                                                              const float *__restrict__ coarse, float *__restrict__ Mall,
+                                                              float *__restrict__ flow_store, int k, int pair_img_mode, int p_base)
+{
+    const int s = lvl_size(k);
+    int x = blockIdx.x * 32 + threadIdx.x, y = blockIdx.y * 8 + threadIdx.y, p = blockIdx.z + p_base;
+    if (x >= s || y >= s) return;
+    int ia = pair_img_mode == 2 ? 2 * p : p, ib = ia + 1;
+    size_t plane = (size_t)s * s, o = (size_t)y * s + x;
+    const float *R0 = Rall + (size_t)ia * PYR_PX * 5 + (size_t)lvl_off(k) * 5;
+    const float *R1 = Rall + (size_t)ib * PYR_PX * 5 + (size_t)lvl_off(k) * 5;
+    float dx = 0.f, dy = 0.f;
+    if (FLOWSRC == 1) {
+        dx = flow[(size_t)p * 2 * plane + o]; dy = flow[(size_t)p * 2 * plane + plane + o];
+    } else if (FLOWSRC == 2) {
+        int cs = s >> 1;
+        const float *cf = coarse + (size_t)p * 2 * cs * cs;
+        dx = up2_sample(cf, cs, x, y); dy = up2_sample(cf + (size_t)cs * cs, cs, x, y);
+    }
+    float m[5];
+    um_pixel(R0, R1, s, x, y, dx, dy, m);
     float *M = Mall + (size_t)p * 5 * T * T;
-    M[o] = r4 * r4 + r6 * r6;
-    M[plane + o] = (r4 + r5) * r6;
-    M[2 * plane + o] = r5 * r5 + r6 * r6;
-    M[3 * plane + o] = r4 * r2 + r6 * r3;
-    M[4 * plane + o] = r6 * r2 + r5 * r3;
+    M[o] = m[0]; M[plane + o] = m[1]; M[2 * plane + o] = m[2]; M[3 * plane + o] = m[3]; M[4 * plane + o] = m[4];
     (void)flow_store;
 }
 
