@@ -78,6 +78,16 @@ def test_audio_edge_cases(eng):
     assert audio.analyze_samples(st, 16000, engine=eng) == audio.analyze_samples(wav[:8000], 16000, engine=eng)
     with pytest.raises(AvdError):
         audio.window_features(np.zeros(48000, np.float32), 48000, engine=eng)   # 24000-sample windows: beyond the kernel's table
+    with pytest.raises(AvdError):
+        audio.window_features(np.zeros(70000, np.float32), 2, engine=eng)       # one-sample windows: more than 65535 of them
+    # a window length that does not factor into two short DFTs (prime): every window takes the direct DFT
+    w2 = (np.random.default_rng(3).integers(-9000, 9001, 3 * 4099 + 17).astype(np.float32) / np.float32(32768))
+    with np.errstate(all="ignore"):
+        want = np.stack(audio_oracle.window_features(w2, 8198), axis=1)                 # sr 8198 -> win 4099 (prime)
+    got = audio.window_features(w2, 8198, engine=eng)
+    assert got.shape == want.shape == (4, 5)
+    assert np.array_equal(got[:, [0, 1, 3]], want[:, [0, 1, 3]]) and np.allclose(got[:, [2, 4]], want[:, [2, 4]], rtol=FEAT_RTOL, atol=0)
+    eng.sync()
 
 
 def test_audio_video_fuse_end_to_end(golden_audio, synth, eng):

@@ -134,3 +134,27 @@ def test_score_clips_argument_errors(eng):
     jl.add(rec_first=0, rec_count=0, npix=0, tlen=3)                  # a clip with no samples: [0.5]*tlen, zero summary
     jobs, sc, vt, fu, bi, pk = scoring.score_jobs(eng, jl, None, 0)
     assert vt[:3].tolist() == [0.5, 0.5, 0.5] and float(sc[0]["texture_var"]) == 0.0 and int(sc[0]["vlen"]) == 3
+
+
+def test_config3_scale_batch(torch, eng, oracle):
+    """BASELINE configs[3]: 256 clips x 10 samples in ONE launch, every clip against the oracle's tail + fuse."""
+    from avd_b200 import fusion, hints as H, scoring
+    from avd_b200._lib import REC_DTYPE
+    rng = np.random.default_rng(11)
+    R = np.concatenate([_random_clip_records(rng, 10, ci) for ci in range(256)])
+    hn = H.compute_hints({"width": 1280, "height": 720, "fps": 30.0, "bit_rate": 2_000_000})
+    jl = scoring.JobList()
+    for ci in range(256):
+        jl.add(rec_first=10 * ci, rec_count=10, npix=1280 * 720, tlen=5, audio=fusion.neutral_audio(5), hints=hn)
+    d_rec = torch.from_numpy(R.view(np.uint8).reshape(-1)).cuda()
+    l0 = eng.launches
+    jobs, sc, vt, fu, bi, pk = scoring.score_jobs(eng, jl, d_rec.data_ptr(), len(R))
+    assert eng.launches == l0 + 1
+    for ci in range(256):
+        r = R[10 * ci:10 * ci + 10]
+        orecs = [{"lap_sum": int(r["lap_sum"][i]), "lap_sumsq": int(r["lap_sumsq"][i]), "ham": int(r["ham_prev"][i]) if i else -1,
+                  **({"flow_mean": float(r["flow_mean"][i]), "flow_var": float(r["flow_var"][i])} if i else {})} for i in range(10)]
+        want_v = oracle.video_result(orecs, 720, 1280, 30.0, 5.0)
+        want_f = oracle.fuse(fusion.neutral_audio(5), want_v, hn, raw=True)
+        assert scoring.video_dict(jobs[ci], sc[ci], vt, 1280, 720, 30.0) == want_v, ci
+        assert scoring.fuse_dict(jobs[ci], sc[ci], fu, bi, pk, hn, with_raw=True) == want_f, ci
