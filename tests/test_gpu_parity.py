@@ -339,3 +339,27 @@ def test_device_path_graph_replay_equals_plain_launches(synth, torch, eng):
             want = eng.analyze_device(frames, prev_frame=prev).cpu().numpy().tobytes()
             got = eng.analyze_device_graph(frames, prev_frame=prev).cpu().numpy().tobytes()
             assert got == want, (prev is not None, rnd)
+
+
+def test_concurrent_calls_from_pool_threads(synth, eng):
+    """api.py:133 runs the analyzer on pool threads, so several requests can be inside the same process-wide engine at
+    once: calls are serialised by the engine's lock and every thread gets the records of its own frames."""
+    import threading
+    clips = [synth.Clip(24, 360, 640, seed=90 + i, events=False) for i in range(4)]
+    batches = [[c[j] for j in (0, 8, 16, 23)] for c in clips]
+    want = [eng.analyze_host(b).tobytes() for b in batches]
+    got, errs = [None] * 4, []
+
+    def work(i):
+        try:
+            for _ in range(5):
+                got[i] = eng.analyze_host(batches[i]).tobytes()
+        except Exception as e:                      # pragma: no cover
+            errs.append(e)
+
+    ts = [threading.Thread(target=work, args=(i,)) for i in range(4)]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join()
+    assert not errs and got == want
