@@ -363,3 +363,25 @@ def test_concurrent_calls_from_pool_threads(synth, eng):
     for t in ts:
         t.join()
     assert not errs and got == want
+
+
+def test_request_batcher_on_device(synth, eng):
+    """service.RequestBatcher with the real engine: eight requests released together, every caller gets the dict it
+    would have got alone, in fewer engine runs."""
+    import threading
+    from avd_b200 import service, video
+    clips = [synth.Clip(60, 360, 640, seed=120 + i, fps=30.0) for i in range(8)]
+    reqs = [(list(c.sampled(15)), {"fps": 30.0, "width": 640, "height": 360, "duration": 2.0}) for c in clips]
+    want = [video.analyze_frames(f, m, engine=eng) for f, m in reqs]
+    b = service.RequestBatcher(engine=eng, max_wait_ms=200.0)
+    got, gate = [None] * 8, threading.Barrier(8)
+
+    def work(i):
+        gate.wait()
+        got[i] = b.analyze_frames(*reqs[i])
+
+    ts = [threading.Thread(target=work, args=(i,)) for i in range(8)]
+    [t.start() for t in ts]
+    [t.join() for t in ts]
+    assert got == want
+    assert sum(b.batches) == 8 and len(b.batches) < 8

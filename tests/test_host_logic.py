@@ -326,3 +326,74 @@ def test_audio_tail_matches_reference(synth):
             assert audio.result_from_features(feats, len(wav), c["sr"]) == c["out"], c["name"]
     bad = audio.analyze("/nonexistent/clip.mp4", {"duration": 2.6})
     assert bad["scores"] == {} and "error" in bad["flags_audio"] and bad["timeline"] == [0.5, 0.5, 0.5]
+
+
+class _OracleEngine:
+    """CPU stand-in for Engine.analyze_host (same record layout, oracle arithmetic) for host-logic tests."""
+    calls = 0
+
+    def analyze_host(self, frames):
+        from avd_b200._lib import REC_DTYPE
+        from oracle import oracle as O
+        type(self).calls += 1
+        out = np.zeros(len(frames), REC_DTYPE)
+        for i, r in enumerate(O.frames_features(list(frames))):
+            out[i]["lap_sum"], out[i]["lap_sumsq"] = r["lap_sum"], r["lap_sumsq"]
+            out[i]["hash"] = r["hash"]; out[i]["ham_prev"] = r["ham"]; out[i]["flags"] = 1 if r["ham"] >= 0 else 0
+            if "flow_mean" in r:
+                out[i]["flow_mean"], out[i]["flow_var"] = r["flow_mean"], r["flow_var"]; out[i]["flags"] |= 2
+        return out
+
+
+def test_request_batcher_coalesces_and_keeps_results(synth):
+    """service.RequestBatcher: requests released together end up in fewer engine runs, each caller gets exactly the
+    result it would have got alone; a request of another frame size goes its own way; an engine failure reaches every
+    caller of the batch."""
+    import threading
+    from avd_b200 import service, video
+    eng = _OracleEngine()
+    clips = [synth.Clip(40, 64, 96, seed=50 + i, events=False) for i in range(4)]
+    reqs = [([c[0], c[20]], {"fps": 30.0, "width": 96, "height": 64, "duration": 1.0 + i}) for i, c in enumerate(clips)]
+    other = synth.Clip(40, 48, 64, seed=60, events=False)
+    reqs.append(([other[0], other[20]], {"fps": 30.0, "duration": 2.0}))
+    want = [video.analyze_frames(f, m, engine=eng) for f, m in reqs]
+    _OracleEngine.calls = 0
+    b = service.RequestBatcher(engine=eng, max_wait_ms=300.0)
+    got, gate = [None] * len(reqs), threading.Barrier(len(reqs))
+
+    def work(i):
+        gate.wait()
+        got[i] = b.analyze_frames(*reqs[i])
+
+    ts = [threading.Thread(target=work, args=(i,)) for i in range(len(reqs))]
+    [t.start() for t in ts]
+    [t.join() for t in ts]
+    assert got == want
+    assert sorted(b.batches) == [1, 4] and _OracleEngine.calls == 2      # four same-size requests in one run, the odd one alone
+
+    class Boom:
+        def analyze_host(self, frames):
+            raise RuntimeError("device lost")
+    bad = service.RequestBatcher(engine=Boom(), max_wait_ms=50.0)
+    errs = []
+
+    def work2(i):
+        try:
+            bad.analyze_frames(*reqs[i])
+        except RuntimeError as e:
+            errs.append(str(e))
+    ts = [threading.Thread(target=work2, args=(i,)) for i in range(3)]
+    [t.start() for t in ts]
+    [t.join() for t in ts]
+    assert errs == ["device lost"] * 3
+
+
+def test_service_analyze_path_neutral_results_without_decoders(tmp_path):
+    """service.analyze_path on a path nothing can open: the video side returns the reference's unopenable-file result
+    (video.py:12-13), the audio side its failure result (audio.py:112-118); fuse still yields a verdict."""
+    from avd_b200 import service
+    out = service.analyze_path(str(tmp_path / "missing.mp4"), {"duration": 3.2, "fps": 30.0, "width": 640, "height": 360, "bit_rate": 500000})
+    assert out["video"] == {"timeline": [], "summary": {}, "timeline_ai": []}      # fuse pads a copy of an empty list (fusion.py:18)
+    assert "error" in out["audio"]["flags_audio"] and out["audio"]["timeline"] == [0.5, 0.5, 0.5]
+    assert set(out) == {"hints", "video", "audio", "result", "timeline_binned", "peaks"}
+    assert out["result"]["label"] in ("real", "uncertain", "ai") and len(out["timeline_binned"]) == 3
