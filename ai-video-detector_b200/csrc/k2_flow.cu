@@ -525,43 +525,6 @@ __global__ void magstats_finalize_kernel(const double *__restrict__ tile_stats, 
     rec[p].flags |= AVD_REC_HAS_FLOW;
 }
 
-// ---- magnitude statistics -----------------------------------------------------------------------------
-__device__ __forceinline__ double block_sum(double v, double *sh)
-{
-    for (int o = 16; o; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
-    int w = threadIdx.x >> 5, l = threadIdx.x & 31;
-    __syncthreads();
-    if (l == 0) sh[w] = v;
-    __syncthreads();
-    if (w == 0) {
-        v = l < (int)(blockDim.x >> 5) ? sh[l] : 0.0;
-        for (int o = 16; o; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
-        if (l == 0) sh[32] = v;
-    }
-    __syncthreads();
-    return sh[32];
-}
-
-__global__ void __launch_bounds__(1024) magstats_kernel(const float *__restrict__ flow, avd_sample_rec *rec, int rec_stride_pairs)
-{
-    __shared__ double sh[33];
-    int p = blockIdx.x;
-    const float *fx = flow + (size_t)p * 2 * T * T, *fy = fx + T * T;
-    double s = 0;
-    for (int i = threadIdx.x; i < T * T; i += blockDim.x) s += (double)sqrtf(fx[i] * fx[i] + fy[i] * fy[i]);
-    float mean = (float)(block_sum(s, sh) / (double)(T * T));
-    double q = 0;
-    for (int i = threadIdx.x; i < T * T; i += blockDim.x) {
-        float d = sqrtf(fx[i] * fx[i] + fy[i] * fy[i]) - mean;
-        q += (double)(d * d);
-    }
-    float var = (float)(block_sum(q, sh) / (double)(T * T));
-    if (threadIdx.x == 0) {
-        avd_sample_rec *r = rec + (size_t)p * rec_stride_pairs;
-        r->flow_mean = mean; r->flow_var = var; r->flags |= AVD_REC_HAS_FLOW;
-    }
-}
-
 __global__ void interleave_kernel(const float *__restrict__ flow, float *__restrict__ out, int n_pairs)
 {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
