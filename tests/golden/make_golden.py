@@ -14,7 +14,7 @@ How the reference is executed, unmodified:
   calcOpticalFlowFarneback) so each stage gets its own golden.  One case additionally goes through a
   real lossless FFV1 .avi and the real cv2.VideoCapture to pin the decode seam.
 
-Inputs are NOT stored: they are regenerated from seeds by ai-video-detector_b200/synth.py (integer-only,
+Inputs are NOT stored: they are regenerated from seeds by avd_b200/synth.py (integer-only,
 machine independent); a sha256 of every generated input is stored so generator drift is detected.
 Library versions used are recorded in the fixture.
 """
@@ -40,7 +40,7 @@ def _load(path, name):
     return m
 
 
-synth = _load(os.path.join(ROOT, "ai-video-detector_b200", "synth.py"), "avd_synth")
+synth = _load(os.path.join(ROOT, "avd_b200", "synth.py"), "avd_synth")
 ref_video = _load(os.path.join(REF, "video.py"), "ref_video")
 ref_fusion = _load(os.path.join(REF, "fusion.py"), "ref_fusion")
 ref_hints = _load(os.path.join(REF, "heuristics_v2.py"), "ref_hints")

@@ -6,7 +6,7 @@
 installed here; only its decode helper uses it).  Its analyze(path, meta) is run unmodified; the one hook is the
 module-level decode helper _extract_wav_16k (audio.py:7-20: ffmpeg + soundfile, both absent here), replaced by a
 function that returns the seeded samples -- exactly what the helper returns to analyze(): (tmp_path, float32 mono, sr).
-Inputs are regenerated from seeds by ai-video-detector_b200/synth.py:audio (integer PCM); their sha256 is stored.
+Inputs are regenerated from seeds by avd_b200/synth.py:audio (integer PCM); their sha256 is stored.
 """
 import hashlib
 import importlib.util
@@ -30,7 +30,7 @@ def _load(path, name):
 
 
 sys.modules.setdefault("soundfile", types.ModuleType("soundfile"))
-synth = _load(os.path.join(ROOT, "ai-video-detector_b200", "synth.py"), "avd_synth")
+synth = _load(os.path.join(ROOT, "avd_b200", "synth.py"), "avd_synth")
 ref_audio = _load(os.path.join(REF, "audio.py"), "ref_audio")
 
 CASES = [  # name, seed, samples, kind, sr

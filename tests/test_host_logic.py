@@ -116,7 +116,7 @@ def test_no_cpu_fallback_without_gpu():
 
 
 def test_product_never_imports_oracle():
-    pkg = os.path.join(ROOT, "ai-video-detector_b200")
+    pkg = os.path.join(ROOT, "avd_b200")
     for dirpath, _, files in os.walk(pkg):
         for f in files:
             if f.endswith((".py", ".cu", ".h", ".cpp")):
