@@ -16,18 +16,17 @@ import tempfile
 
 import numpy as np
 
-from .engine import default_engine
+from .engine import lease
 
 
 def window_features(wav: np.ndarray, sr: int, engine=None) -> np.ndarray:
     """(n_windows, 5) float64: rms, zcr, flat, roll, sc per 0.5 s window (audio.py:38-61), computed on the device."""
-    eng = engine or default_engine()
     wav = np.ascontiguousarray(wav, dtype=np.float32)
     win = max(1, int(sr * 0.5)) if sr else 1
     nwin = (len(wav) + win - 1) // win
     feats = np.zeros((nwin, 5), np.float64)
     if nwin:
-        with eng._lock:
+        with lease(engine) as eng, eng._lock:
             eng._check(eng.L.avd_audio_windows(eng.h, C.c_void_p(wav.ctypes.data), len(wav), win,
                                                C.c_void_p(feats.ctypes.data), None), "avd_audio_windows")
     return feats

@@ -126,6 +126,7 @@ int avd_ensure(avd_ctx *ctx, void **p, size_t *cap, size_t need)
 {
     if (*cap >= need) return AVD_OK;
     if (*p) { cudaFree(*p); *p = nullptr; *cap = 0; }
+    ctx->ws_generation++;            // cached CUDA graphs hold the old address: callers key their caches on this
     size_t want = need + need / 8;
     if (cudaMalloc(p, want) != cudaSuccess) {
         cudaGetLastError();
@@ -199,8 +200,10 @@ void avd_destroy(avd_ctx *ctx)
     cudaSetDevice(ctx->device);
     cudaDeviceSynchronize();
     for (auto &kv : ctx->tables) cudaFree(kv.second);
-    cudaFree(ctx->gray); cudaFree(ctx->area_rows); cudaFree(ctx->k2_ws); cudaFree(ctx->ring);
+    cudaFree(ctx->gray); cudaFree(ctx->area_rows); cudaFree(ctx->k2_ws); cudaFree(ctx->ring); cudaFree(ctx->bgr_slot);
     cudaFree(ctx->thumbs); cudaFree(ctx->recs); cudaFree(ctx->area32); cudaFree(ctx->fixlist); cudaFree(ctx->k3_ws); cudaFree(ctx->k4_ws);
+    for (void *h : ctx->host_allocs) cudaFreeHost(h);
+    ctx->host_allocs.clear();
     for (int i = 0; i < 4; i++) { cudaEventDestroy(ctx->ev_copied[i]); cudaEventDestroy(ctx->ev_free[i]); }
     cudaStreamDestroy(ctx->compute); cudaStreamDestroy(ctx->copy);
     cudaGetLastError();
@@ -222,16 +225,20 @@ void *avd_host_alloc(avd_ctx *ctx, size_t bytes)
     void *p = nullptr;
     if (!ctx || cudaSetDevice(ctx->device) != cudaSuccess) return nullptr;
     if (cudaHostAlloc(&p, bytes, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); ctx->err = "cudaHostAlloc failed"; return nullptr; }
+    ctx->host_allocs.insert(p);
     return p;
 }
 
 void avd_host_free(avd_ctx *ctx, void *p)
 {
-    (void)ctx;
-    if (p) cudaFreeHost(p);
+    if (!p) return;
+    if (ctx) ctx->host_allocs.erase(p);
+    cudaFreeHost(p);
 }
 
 uint64_t avd_launch_count(const avd_ctx *ctx) { return ctx ? ctx->launches : 0; }
+uint64_t avd_ws_generation(const avd_ctx *ctx) { return ctx ? ctx->ws_generation : 0; }
+size_t avd_host_alloc_count(const avd_ctx *ctx) { return ctx ? ctx->host_allocs.size() : 0; }
 
 int avd_profile_enable(avd_ctx *ctx, int on)
 {
@@ -372,68 +379,129 @@ int avd_gray(avd_ctx *ctx, const uint8_t *d_bgr, int H, int W, size_t row_pitch,
     return k1_gray_only(ctx, d_bgr, H, W, row_pitch, d_gray, (cudaStream_t)stream);
 }
 
-// Host streaming pipeline.  Frames go to a ring of device slots on the copy stream; K1 consumes a slot on
-// the compute stream as soon as its copy lands; K2 runs per chunk on the thumbnails produced so far, so
-// PCIe transfer, the per-frame kernel and the flow kernels overlap.
-int avd_analyze_host(avd_ctx *ctx, const uint8_t *const *h_frames, int n, int H, int W, size_t row_pitch,
-                     avd_sample_rec *h_rec)
+// Host streaming pipeline.  Frames go to a ring of device slots on the copy stream; the compute stream converts
+// (YUV input) and runs K1 on a slot as soon as its copy lands; K2 runs on the thumbnails accumulated so far whenever at
+// least k2_min pairs are pending (and once more at the end), so PCIe transfer, the per-frame kernel and the flow
+// kernels overlap while K2 still gets batches large enough to fill the GPU.
+static int analyze_host_impl(avd_ctx *ctx, const uint8_t *const *h_frames, int n, int H, int W, size_t row_pitch, int fmt,
+                             avd_sample_rec *h_rec)
 {
-    if (!ctx) return AVD_ERR_ARG;
-    int rc = check_shape(ctx, n, H, W, row_pitch);
-    if (rc) return rc;
-    if (n == 0) return AVD_OK;
-    if (!h_frames) { ctx->err = "null buffer"; return AVD_ERR_ARG; }
-    ctx->recs_n = 0;
-    AVD_CUDA(ctx, cudaSetDevice(ctx->device));
-    // device frame layout inside a slot: dense rows padded to 16 bytes so the fused kernel applies
-    size_t dpitch = ((size_t)W * 3 + 15) & ~(size_t)15;
-    size_t fbytes = dpitch * H;
+    int rc;
+    const bool yuv = fmt != AVD_FMT_BGR24;
+    // device frame layout inside a BGR slot: dense rows padded to 16 bytes so the streaming kernel applies
+    const size_t dpitch = ((size_t)W * 3 + 15) & ~(size_t)15;
+    const size_t fbytes = dpitch * H;
+    const size_t ybytes = (size_t)W * H * 3 / 2;                    // dense I420 frame
+    const size_t ubytes = yuv ? ybytes : fbytes;                    // bytes uploaded per frame
     const int SLOTS = 3;
     int per_slot = (int)((112u << 20) / fbytes);
     if (per_slot < 1) per_slot = 1;
     static const int max_slot = getenv("AVD_HOST_CHUNK") ? atoi(getenv("AVD_HOST_CHUNK")) : 16;   // frames per device slot (tuning)
+    static const int k2_min = getenv("AVD_HOST_K2_MIN") ? atoi(getenv("AVD_HOST_K2_MIN")) : 40;   // pairs per K2 batch (tuning)
     if (per_slot > max_slot) per_slot = max_slot < 1 ? 1 : max_slot;
     if (per_slot > n) per_slot = n;
-    if ((rc = avd_ensure(ctx, (void **)&ctx->ring, &ctx->ring_cap, (size_t)SLOTS * per_slot * fbytes))) return rc;
+    if ((rc = avd_ensure(ctx, (void **)&ctx->ring, &ctx->ring_cap, (size_t)SLOTS * per_slot * ubytes))) return rc;
+    if (yuv && (rc = avd_ensure(ctx, (void **)&ctx->bgr_slot, &ctx->bgr_slot_cap, (size_t)per_slot * fbytes))) return rc;
     if ((rc = avd_ensure(ctx, (void **)&ctx->thumbs, &ctx->thumbs_cap, (size_t)n * AVD_T * AVD_T))) return rc;
     if ((rc = avd_ensure(ctx, (void **)&ctx->recs, &ctx->recs_cap, (size_t)n * sizeof(avd_sample_rec)))) return rc;
     if ((rc = avd_ensure(ctx, (void **)&ctx->area32, &ctx->area32_cap, (size_t)n * 1024))) return rc;
+    if ((rc = k2_reserve(ctx, n - 1))) return rc;                   // no workspace growth while the pipeline is in flight
     const ShapeTables *tab, *htab;
     if ((rc = avd_get_tables(ctx, H, W, &tab, &htab))) return rc;
-    int chunk = 0;
+    int chunk = 0, k2_done = 0;                                     // k2_done: thumbnails whose flow statistics are issued
     for (int f0 = 0; f0 < n; f0 += per_slot, chunk++) {
-        int nb = n - f0 < per_slot ? n - f0 : per_slot;
-        int slot = chunk % SLOTS;
-        uint8_t *dst = ctx->ring + (size_t)slot * per_slot * fbytes;
+        const int nb = n - f0 < per_slot ? n - f0 : per_slot;
+        const int slot = chunk % SLOTS;
+        uint8_t *up = ctx->ring + (size_t)slot * per_slot * ubytes;
         if (chunk >= SLOTS) AVD_CUDA(ctx, cudaStreamWaitEvent(ctx->copy, ctx->ev_free[slot], 0));
-        for (int j = 0; j < nb; j++)
-            if (!h_frames[f0 + j]) { ctx->err = "null frame pointer"; cudaStreamSynchronize(ctx->copy); cudaStreamSynchronize(ctx->compute); return AVD_ERR_ARG; }
         for (int j = 0; j < nb;) {
-            if (dpitch == row_pitch) {
+            if (yuv || dpitch == row_pitch) {
                 // frames that sit back to back in host memory (one decoded batch) go as one copy: fewer, larger DMA requests
                 int run = 1;
-                while (j + run < nb && h_frames[f0 + j + run] == h_frames[f0 + j + run - 1] + fbytes) run++;
-                AVD_CUDA(ctx, cudaMemcpyAsync(dst + (size_t)j * fbytes, h_frames[f0 + j], fbytes * run, cudaMemcpyHostToDevice, ctx->copy));
+                while (j + run < nb && h_frames[f0 + j + run] == h_frames[f0 + j + run - 1] + ubytes) run++;
+                AVD_CUDA(ctx, cudaMemcpyAsync(up + (size_t)j * ubytes, h_frames[f0 + j], ubytes * run, cudaMemcpyHostToDevice, ctx->copy));
                 j += run;
             } else {
-                AVD_CUDA(ctx, cudaMemcpy2DAsync(dst + (size_t)j * fbytes, dpitch, h_frames[f0 + j], row_pitch, (size_t)W * 3, H,
+                AVD_CUDA(ctx, cudaMemcpy2DAsync(up + (size_t)j * fbytes, dpitch, h_frames[f0 + j], row_pitch, (size_t)W * 3, H,
                                                cudaMemcpyHostToDevice, ctx->copy));
                 j++;
             }
         }
         AVD_CUDA(ctx, cudaEventRecord(ctx->ev_copied[slot], ctx->copy));
         AVD_CUDA(ctx, cudaStreamWaitEvent(ctx->compute, ctx->ev_copied[slot], 0));
+        const uint8_t *bgr = up;
+        if (yuv) {
+            if ((rc = k0_yuv420_to_bgr(ctx, up, ybytes, nb, H, W, fmt == AVD_FMT_J420, ctx->bgr_slot, dpitch, fbytes, ctx->compute))) return rc;
+            AVD_CUDA(ctx, cudaEventRecord(ctx->ev_free[slot], ctx->compute));    // the upload slot is free once converted
+            bgr = ctx->bgr_slot;
+        }
         avd_sample_rec *rec = ctx->recs + f0;
         uint8_t *th = ctx->thumbs + (size_t)f0 * AVD_T * AVD_T;
         const uint32_t *prev_hash = f0 > 0 ? ctx->recs[f0 - 1].hash : nullptr;
-        if ((rc = avd_frames_features(ctx, dst, nb, H, W, dpitch, fbytes, prev_hash, rec, th, ctx->area32 + (size_t)f0 * 1024, ctx->compute))) return rc;
-        AVD_CUDA(ctx, cudaEventRecord(ctx->ev_free[slot], ctx->compute));
-        if ((rc = avd_flow_stats(ctx, th, nb, f0 > 0 ? th - (size_t)AVD_T * AVD_T : nullptr, rec, ctx->compute))) return rc;
+        if ((rc = avd_frames_features(ctx, bgr, nb, H, W, dpitch, fbytes, prev_hash, rec, th, ctx->area32 + (size_t)f0 * 1024, ctx->compute))) return rc;
+        if (!yuv) AVD_CUDA(ctx, cudaEventRecord(ctx->ev_free[slot], ctx->compute));
+        const int ready = f0 + nb, last = ready == n;
+        const int pending = ready - k2_done - (k2_done == 0 ? 1 : 0);            // pairs not yet issued
+        if (pending > 0 && (last || pending >= k2_min)) {
+            const uint8_t *t0 = ctx->thumbs + (size_t)k2_done * AVD_T * AVD_T;
+            if ((rc = avd_flow_stats(ctx, t0, ready - k2_done, k2_done > 0 ? t0 - (size_t)AVD_T * AVD_T : nullptr, ctx->recs + k2_done, ctx->compute))) return rc;
+            k2_done = ready;
+        }
     }
     if (h_rec) AVD_CUDA(ctx, cudaMemcpyAsync(h_rec, ctx->recs, (size_t)n * sizeof(avd_sample_rec), cudaMemcpyDeviceToHost, ctx->compute));
     AVD_CUDA(ctx, cudaStreamSynchronize(ctx->compute));
     ctx->recs_n = n;
     return AVD_OK;
+}
+
+static int analyze_host_checked(avd_ctx *ctx, const uint8_t *const *h_frames, int n, int H, int W, size_t row_pitch, int fmt,
+                                avd_sample_rec *h_rec)
+{
+    if (!ctx) return AVD_ERR_ARG;
+    int rc = check_shape(ctx, n, H, W, row_pitch);
+    if (rc) return rc;
+    if (fmt != AVD_FMT_BGR24 && fmt != AVD_FMT_I420 && fmt != AVD_FMT_J420) { ctx->err = "unknown frame format"; return AVD_ERR_ARG; }
+    if (fmt != AVD_FMT_BGR24 && ((H | W) & 1)) { ctx->err = "4:2:0 input needs even width and height"; return AVD_ERR_ARG; }
+    if (n == 0) return AVD_OK;
+    if (!h_frames) { ctx->err = "null buffer"; return AVD_ERR_ARG; }
+    for (int i = 0; i < n; i++)
+        if (!h_frames[i]) { ctx->err = "null frame pointer"; return AVD_ERR_ARG; }
+    ctx->recs_n = 0;
+    AVD_CUDA(ctx, cudaSetDevice(ctx->device));
+    rc = analyze_host_impl(ctx, h_frames, n, H, W, row_pitch, fmt, h_rec);
+    if (rc) {
+        // single error exit: copies from the caller's staging memory may still be in flight -- the caller is free to reuse
+        // that memory as soon as we return, so drain both streams first (and clear a sticky launch error)
+        cudaStreamSynchronize(ctx->copy);
+        cudaStreamSynchronize(ctx->compute);
+        cudaGetLastError();
+    }
+    return rc;
+}
+
+int avd_analyze_host(avd_ctx *ctx, const uint8_t *const *h_frames, int n, int H, int W, size_t row_pitch,
+                     avd_sample_rec *h_rec)
+{
+    return analyze_host_checked(ctx, h_frames, n, H, W, row_pitch, AVD_FMT_BGR24, h_rec);
+}
+
+int avd_analyze_host_yuv420(avd_ctx *ctx, const uint8_t *const *h_frames, int n, int H, int W, int full_range,
+                            avd_sample_rec *h_rec)
+{
+    return analyze_host_checked(ctx, h_frames, n, H, W, (size_t)W * 3, full_range ? AVD_FMT_J420 : AVD_FMT_I420, h_rec);
+}
+
+int avd_yuv420_to_bgr(avd_ctx *ctx, const uint8_t *d_yuv, size_t yuv_frame_stride, int n, int H, int W, int full_range,
+                      uint8_t *d_bgr, size_t row_pitch, size_t frame_stride, void *stream)
+{
+    if (!ctx) return AVD_ERR_ARG;
+    int rc = check_shape(ctx, n, H, W, row_pitch);
+    if (rc) return rc;
+    if ((H | W) & 1) { ctx->err = "4:2:0 input needs even width and height"; return AVD_ERR_ARG; }
+    if (n == 0) return AVD_OK;
+    if (!d_yuv || !d_bgr || yuv_frame_stride < (size_t)W * H * 3 / 2 || frame_stride < row_pitch * (size_t)H) { ctx->err = "null buffer or stride too small"; return AVD_ERR_ARG; }
+    AVD_CUDA(ctx, cudaSetDevice(ctx->device));
+    return k0_yuv420_to_bgr(ctx, d_yuv, yuv_frame_stride, n, H, W, full_range != 0, d_bgr, row_pitch, frame_stride, (cudaStream_t)stream);
 }
 
 #pragma GCC visibility pop

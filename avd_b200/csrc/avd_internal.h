@@ -4,12 +4,16 @@
 #include <stdint.h>
 #include <string>
 #include <map>
+#include <set>
 #include <utility>
 #include <vector>
 #include "../../include/avd.h"
 
 #define AVD_D 32            // aHash side
 #define AVD_T 320           // thumbnail side
+#define AVD_FMT_BGR24 0
+#define AVD_FMT_I420 1         // yuv420p, limited range (H.264 / HEVC / MPEG-4 decoders)
+#define AVD_FMT_J420 2         // yuvj420p, full range (MJPEG)
 #define AVD_LEVELS 4        // Farneback pyramid: 40, 80, 160, 320
 
 // One INTER_AREA destination cell along one axis (OpenCV computeResizeAreaTab, restated):
@@ -51,6 +55,8 @@ struct avd_ctx {
     cudaStream_t compute = nullptr, copy = nullptr;
     std::string err;
     uint64_t launches = 0;
+    uint64_t ws_generation = 0;                            // bumped whenever a grow-only device buffer moves (avd_ensure)
+    std::set<void *> host_allocs;                          // avd_host_alloc regions not yet freed (released by avd_destroy)
     int k1_mode = 0;
     std::map<std::pair<int, int>, ShapeTables *> tables;   // device pointers
     std::map<std::pair<int, int>, ShapeTables> tables_host;
@@ -61,6 +67,7 @@ struct avd_ctx {
     void *k2_ws = nullptr; size_t k2_ws_cap = 0; int k2_batch = 0;
     // host streaming ring (avd_analyze_host)
     uint8_t *ring = nullptr; size_t ring_cap = 0;
+    uint8_t *bgr_slot = nullptr; size_t bgr_slot_cap = 0;   // YUV input: the converted frames of the slot in flight
     cudaEvent_t ev_copied[4] = {}, ev_free[4] = {};
     uint8_t *thumbs = nullptr; size_t thumbs_cap = 0;
     avd_sample_rec *recs = nullptr; size_t recs_cap = 0; int recs_n = 0;   // recs_n: records of the last host run
@@ -129,6 +136,10 @@ int k1_banded(avd_ctx *ctx, const uint8_t *d_bgr, int n, int H, int W, size_t pi
 int k1_fused(avd_ctx *ctx, const uint8_t *d_bgr, int n, int H, int W, size_t pitch, size_t fstride,
              const ShapeTables *tab, const ShapeTables *htab, avd_sample_rec *d_rec, uint8_t *d_thumbs,
              uint8_t *d_area32, uint32_t *d_fixlist, cudaStream_t st);
+// k0_yuv.cu: dense I420 frames (Y HxW, U, V (H/2)x(W/2)) -> packed BGR, swscale's unscaled yuv420p->bgr24 arithmetic
+int k0_yuv420_to_bgr(avd_ctx *ctx, const uint8_t *d_yuv, size_t yuv_stride, int n, int H, int W, bool full_range,
+                     uint8_t *d_bgr, size_t pitch, size_t fstride, cudaStream_t st);
 // k2_flow.cu
+int k2_reserve(avd_ctx *ctx, int n_pairs);   // size the workspace for runs of up to n_pairs pairs now
 int k2_flow(avd_ctx *ctx, const uint8_t *d_prev, const uint8_t *d_next, size_t prev_stride, size_t next_stride,
             int n_pairs, bool shared_chain, avd_sample_rec *d_rec_first, float *d_flow_out, cudaStream_t st);

@@ -574,6 +574,13 @@ static size_t k2_ws_bytes(int ni, int np)
     return sizeof(float) * ((size_t)ni * PYR_PX * 6 + (size_t)np * T * T * 9) + sizeof(double) * 2 * STAT_TILES_MAX * (size_t)np;
 }
 
+int k2_reserve(avd_ctx *ctx, int n_pairs)
+{
+    if (n_pairs <= 0) return AVD_OK;
+    const int cap_np = n_pairs < 128 ? n_pairs : 128;
+    return avd_ensure(ctx, &ctx->k2_ws, &ctx->k2_ws_cap, k2_ws_bytes(cap_np + 1, cap_np));
+}
+
 int k2_flow(avd_ctx *ctx, const uint8_t *d_prev, const uint8_t *d_next, size_t prev_stride, size_t next_stride,
             int n_pairs, bool shared_chain, avd_sample_rec *d_rec_first, float *d_flow_out, cudaStream_t st)
 {

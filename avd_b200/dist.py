@@ -59,12 +59,19 @@ def analyze_frames_sharded(local_frames, halo_frame, n_total: int, meta: dict, r
     result (the tail is O(samples) host arithmetic)."""
     from . import video
     frames = ([halo_frame] if halo_frame is not None else []) + list(local_frames)
+    if H is None or W is None:
+        # a rank whose shard is empty (n_total < world) has no frame to read the shape from and would fail *before* the
+        # collective while the others wait in it: make that an error on every rank, before any communication
+        if n_total < world:
+            raise ValueError("analyze_frames_sharded: pass H and W when n_total < world (some ranks hold no frames)")
+        if not frames:
+            raise ValueError("analyze_frames_sharded: this rank has no frames; pass H and W")
     recs = records_fn(frames) if frames else np.zeros(0, REC_DTYPE)
     if halo_frame is not None:
         recs = recs[1:]
     full = gather_records(recs, n_total, rank, world, device)
     fps = meta.get("fps") or 0.0
-    if H is None:
+    if H is None or W is None:
         H, W = int(frames[0].shape[0]), int(frames[0].shape[1])
     duration = meta.get("duration") or (n_total * video.sample_step(fps) / fps if fps > 0 else 0.0)
     return video.result_from_records(full, H, W, fps, duration, w=meta.get("width") or W, h=meta.get("height") or H), full

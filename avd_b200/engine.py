@@ -6,9 +6,12 @@ them.  The host entry point (`analyze_host`) is torch-free: NumPy frames in, Num
 """
 from __future__ import annotations
 
+import contextlib
 import ctypes as C
 import json
+import os
 import threading
+from collections import OrderedDict
 
 import numpy as np
 
@@ -26,15 +29,22 @@ class Engine:
         if rc != 0:
             raise AvdError(f"avd_create(device={device}) failed with status {rc} (needs an sm_100 GPU)")
         self.h, self.device = h, int(device)
-        self._lock = threading.Lock()   # a context is single-threaded (include/avd.h)
-        self._graphs = {}
+        self._lock = threading.RLock()  # a context is single-threaded (include/avd.h); re-entrant so that a caller can hold
+        #                                 it across several entry points that share context state (scoring.score_clip_batch)
+        self._graphs = OrderedDict()    # CUDA graphs of the device path, LRU, keyed by buffers + workspace generation
+        self._staging = {}              # nbytes -> free pinned staging buffers (reused across calls, freed with the context)
 
     # -- plumbing ------------------------------------------------------------------------------------
     graph_launches = 0           # kernel launches replayed through CUDA graphs (not seen by avd_launch_count)
 
+    GRAPH_CACHE = 8              # cached graphs per engine
+    STAGING_CACHE_BYTES = 4 << 30   # pinned bytes kept for reuse per engine; beyond that, returned buffers are freed
+
     def close(self):
-        if self._graphs:
+        if getattr(self, "_graphs", None):
             self._graphs.clear()
+        if getattr(self, "_staging", None):
+            self._staging.clear()         # the regions themselves are released by avd_destroy
         if getattr(self, "h", None):
             self.L.avd_destroy(self.h)
             self.h = None
@@ -56,6 +66,11 @@ class Engine:
     def launches(self) -> int:
         return int(self.L.avd_launch_count(self.h))
 
+    @property
+    def ws_generation(self) -> int:
+        """Bumped by the library whenever one of its scratch buffers moves (include/avd.h: avd_ws_generation)."""
+        return int(self.L.avd_ws_generation(self.h))
+
     def set_k1_mode(self, mode: int):
         self._check(self.L.avd_set_k1_mode(self.h, int(mode)), "avd_set_k1_mode")
 
@@ -68,13 +83,46 @@ class Engine:
         return json.loads(buf.value.decode())
 
     def pinned(self, shape, dtype=np.uint8) -> np.ndarray:
-        """Page-locked host array (cudaHostAlloc) for full-rate cudaMemcpyAsync; freed with the engine."""
-        n = int(np.prod(shape)) * np.dtype(dtype).itemsize
-        p = self.L.avd_host_alloc(self.h, n)
+        """Page-locked host array (cudaHostAlloc) for full-rate cudaMemcpyAsync.  The region lives until
+        `free_pinned(array)` or until the engine is closed (avd_destroy releases what is left) -- long-lived callers
+        that need a scratch buffer per call should use `staging()` instead, which reuses regions."""
+        n = max(1, int(np.prod(shape)) * np.dtype(dtype).itemsize)
+        with self._lock:
+            p = self.L.avd_host_alloc(self.h, n)
         if not p:
-            raise AvdError("avd_host_alloc failed")
+            raise AvdError(f"avd_host_alloc({n} bytes) failed")
         buf = (C.c_uint8 * n).from_address(p)
-        return np.frombuffer(buf, dtype=dtype).reshape(shape)
+        return np.frombuffer(buf, dtype=dtype)[:int(np.prod(shape))].reshape(shape)
+
+    def free_pinned(self, arr: np.ndarray):
+        with self._lock:
+            self.L.avd_host_free(self.h, C.c_void_p(arr.ctypes.data))
+
+    @property
+    def pinned_regions(self) -> int:
+        """Live cudaHostAlloc regions of this context (leak checks)."""
+        return int(self.L.avd_host_alloc_count(self.h))
+
+    @contextlib.contextmanager
+    def staging(self, nbytes: int):
+        """A pinned uint8 scratch buffer of `nbytes` for the duration of the `with` block.  Buffers are cached per
+        size and handed out again by later calls, so a server calling `video.analyze` per request allocates pinned memory
+        once per frame size, not once per request."""
+        nbytes = int(nbytes)
+        with self._lock:
+            free = self._staging.get(nbytes)
+            buf = free.pop() if free else None
+        if buf is None:
+            buf = self.pinned((nbytes,))
+        try:
+            yield buf
+        finally:
+            with self._lock:
+                cached = sum(k * len(v) for k, v in self._staging.items())
+                if self.h and cached + nbytes <= self.STAGING_CACHE_BYTES:
+                    self._staging.setdefault(nbytes, []).append(buf)
+                elif self.h:
+                    self.L.avd_host_free(self.h, C.c_void_p(buf.ctypes.data))
 
     @staticmethod
     def _stream():
@@ -117,6 +165,17 @@ class Engine:
                                                C.c_void_p(out.data_ptr()), self._stream()), "avd_flow_fields")
         return out
 
+    def yuv420_to_bgr(self, yuv, H: int, W: int, full_range: bool = False, pitch: int = 0):
+        """K0 on (n, 1.5*H*W) uint8 CUDA tensor of dense I420 frames -> (n, H, pitch) uint8 packed BGR rows."""
+        import torch
+        n = yuv.shape[0]
+        pitch = int(pitch) or 3 * W
+        out = torch.zeros((n, H, pitch), dtype=torch.uint8, device=yuv.device)
+        with self._lock:
+            self._check(self.L.avd_yuv420_to_bgr(self.h, C.c_void_p(yuv.data_ptr()), yuv.stride(0), n, H, W, int(bool(full_range)),
+                                                 C.c_void_p(out.data_ptr()), pitch, H * pitch, self._stream()), "avd_yuv420_to_bgr")
+        return out
+
     def gray(self, frame):
         import torch
         H, W, _ = frame.shape
@@ -146,37 +205,66 @@ class Engine:
         The inputs must stay at the same addresses between calls (a resident batch, a reused staging buffer); the
         returned record tensor is owned by the graph and overwritten by the next call."""
         import torch
-        key = (frames.data_ptr(), tuple(frames.shape), tuple(frames.stride()),
-               None if prev_frame is None else prev_frame.data_ptr())
-        g = self._graphs.get(key)
-        if g is None:
-            side = torch.cuda.Stream()
-            side.wait_stream(torch.cuda.current_stream())
-            with torch.cuda.stream(side):
-                self.analyze_device(frames, prev_frame)      # warm-up: tables, workspaces, function attributes
-            torch.cuda.current_stream().wait_stream(side)
-            torch.cuda.synchronize()
-            graph = torch.cuda.CUDAGraph()
-            l0 = self.launches
-            with torch.cuda.graph(graph):
-                rec = self.analyze_device(frames, prev_frame)
-            g = self._graphs[key] = (graph, rec, self.launches - l0)
-        g[0].replay()
-        self.graph_launches += g[2]
-        return g[1]
+        with self._lock:
+            key = (frames.data_ptr(), tuple(frames.shape), tuple(frames.stride()),
+                   None if prev_frame is None else prev_frame.data_ptr())
+            g = self._graphs.get(key)
+            # a graph holds the addresses of the library's grow-only scratch buffers: when any of them has moved since the
+            # capture (a later call with more frames, another shape, analyze_host on this engine ...) it must not be replayed
+            if g is not None and g[3] != self.ws_generation:
+                del self._graphs[key]
+                g = None
+            if g is None:
+                side = torch.cuda.Stream()
+                side.wait_stream(torch.cuda.current_stream())
+                with torch.cuda.stream(side):
+                    self.analyze_device(frames, prev_frame)      # warm-up: tables, workspaces, function attributes
+                torch.cuda.current_stream().wait_stream(side)
+                torch.cuda.synchronize()
+                graph = torch.cuda.CUDAGraph()
+                l0, gen = self.launches, self.ws_generation
+                with torch.cuda.graph(graph):
+                    rec = self.analyze_device(frames, prev_frame)
+                if self.ws_generation != gen:
+                    raise AvdError("workspace moved during graph capture")     # cannot happen after the warm-up run
+                g = self._graphs[key] = (graph, rec, self.launches - l0, gen)
+                while len(self._graphs) > self.GRAPH_CACHE:
+                    self._graphs.popitem(last=False)
+            else:
+                self._graphs.move_to_end(key)
+            g[0].replay()
+            self.graph_launches += g[2]
+            return g[1]
 
     @staticmethod
     def records_to_numpy(rec) -> np.ndarray:
         return rec.cpu().numpy().view(REC_DTYPE).reshape(-1)
 
     # -- host path (the public, torch-free call) --------------------------------------------------------
-    def analyze_host(self, frames, keep_on_device: bool = False):
+    def analyze_host(self, frames, keep_on_device: bool = False, fmt: str = "bgr", shape=None):
         """frames: sequence of (H,W,3) uint8 arrays (same shape, rows contiguous) or one (n,H,W,3) array,
         ideally in pinned memory (`Engine.pinned`).  Streams them through K1/K2 and returns records.
-        keep_on_device: leave the records in HBM for `scoring.score_jobs` (K3) and return None."""
+        keep_on_device: leave the records in HBM for `scoring.score_jobs` (K3) and return None.
+        fmt "i420" / "j420" (with shape=(H, W)): every frame is a dense planar 4:2:0 picture of 1.5*H*W bytes as the
+        decoder emits it (limited / full range); the colour conversion of cv2's retrieve() then runs on the device."""
         n = len(frames)
         out = None if keep_on_device else np.zeros(n, REC_DTYPE)
         if n == 0:
+            return out
+        if fmt != "bgr":
+            if fmt not in ("i420", "j420") or shape is None:
+                raise AvdError("analyze_host: fmt must be 'bgr', 'i420' or 'j420' (the latter two with shape=(H, W))")
+            H, W = int(shape[0]), int(shape[1])
+            ptrs = (C.c_void_p * n)()
+            for i in range(n):
+                f = frames[i]
+                if f.dtype != np.uint8 or f.size != H * W * 3 // 2 or not f.flags["C_CONTIGUOUS"]:
+                    raise AvdError("analyze_host: 4:2:0 frames must be contiguous uint8 arrays of 1.5*H*W bytes")
+                ptrs[i] = f.ctypes.data
+            with self._lock:
+                self._check(self.L.avd_analyze_host_yuv420(self.h, ptrs, n, H, W, int(fmt == "j420"),
+                                                           C.c_void_p(out.ctypes.data) if out is not None else None),
+                            "avd_analyze_host_yuv420")
             return out
         f0 = frames[0]
         H, W = int(f0.shape[0]), int(f0.shape[1])
@@ -193,13 +281,74 @@ class Engine:
         return out
 
 
-_default = {}
-_default_lock = threading.Lock()
+# ---- process-wide engines ------------------------------------------------------------------------------------
+# The reference runs its analyzer on pool threads (api.py:133), so several requests can be inside video.analyze at once.
+# A context is single-threaded; instead of serialising every request on one context, each device has a small pool of
+# contexts (own streams, own workspaces) and a request leases one for its duration: concurrent small requests then
+# overlap on the GPU (the Farneback levels of a short clip are latency-bound and leave most SMs idle).
+POOL_SIZE = max(1, int(os.environ.get("AVD_ENGINES_PER_DEVICE", "4")))
+
+
+class EnginePool:
+    def __init__(self, device: int = 0, size: int = POOL_SIZE):
+        self.device, self.size = int(device), int(size)
+        self._cv = threading.Condition()
+        self._free, self._all = [], []
+
+    @contextlib.contextmanager
+    def lease(self):
+        with self._cv:
+            while not self._free and len(self._all) >= self.size:
+                self._cv.wait()
+            if self._free:
+                eng = self._free.pop()
+            else:
+                eng = Engine(self.device)
+                self._all.append(eng)
+        try:
+            yield eng
+        finally:
+            with self._cv:
+                self._free.append(eng)
+                self._cv.notify()
+
+    def first(self) -> Engine:
+        with self._cv:
+            if not self._all:
+                eng = Engine(self.device)
+                self._all.append(eng)
+                self._free.append(eng)
+            return self._all[0]
+
+    def close(self):
+        with self._cv:
+            for e in self._all:
+                e.close()
+            self._all, self._free = [], []
+
+
+_pools = {}
+_pools_lock = threading.Lock()
+
+
+def engine_pool(device: int = 0) -> EnginePool:
+    with _pools_lock:
+        if device not in _pools:
+            _pools[device] = EnginePool(device)
+        return _pools[device]
 
 
 def default_engine(device: int = 0) -> Engine:
-    """Process-wide engine per device (created lazily)."""
-    with _default_lock:
-        if device not in _default:
-            _default[device] = Engine(device)
-        return _default[device]
+    """The first engine of the device's pool (created lazily).  Calls on it are serialised by its lock; request handlers
+    should use `lease()`."""
+    return engine_pool(device).first()
+
+
+@contextlib.contextmanager
+def lease(engine=None, device: int = 0):
+    """`with lease(engine) as eng:` -- the given engine, or one leased from the device's pool for the block."""
+    if engine is not None:
+        yield engine
+    else:
+        with engine_pool(device).lease() as eng:
+            yield eng

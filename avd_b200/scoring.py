@@ -146,9 +146,12 @@ def score_clip_batch(engine, clips, metas, audios=None, hints=None, with_raw: bo
                audio=None if audios is None else audios[ci], hints=None if hints is None else hints[ci])
         info.append((meta.get("width") or W, meta.get("height") or H, fps))
         frames.extend(c[i] for i in range(n))
-    if frames:
-        engine.analyze_host(frames, keep_on_device=True)
-    jobs, scores, vt, fu, bi, pk = score_jobs(engine, jl, None, len(frames))
+    # the records of the host run stay in the context's own buffer: nobody else may run on this context between the
+    # two calls (the engine's lock is re-entrant)
+    with engine._lock:
+        if frames:
+            engine.analyze_host(frames, keep_on_device=True)
+        jobs, scores, vt, fu, bi, pk = score_jobs(engine, jl, None, len(frames))
     out = []
     for ci in range(len(clips)):
         v = video_dict(jobs[ci], scores[ci], vt, *info[ci])

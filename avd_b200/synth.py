@@ -114,6 +114,24 @@ def noise_frames(n: int, H: int, W: int, seed: int) -> np.ndarray:
     return rng.integers(0, 256, (n, H, W, 3), dtype=np.uint8)
 
 
+def bgr_to_i420(bgr: np.ndarray) -> np.ndarray:
+    """Synthetic *decoder output*: a dense planar 4:2:0 picture (H*W luma bytes, then the (H/2)x(W/2) U and V planes) made
+    from a BGR frame with the usual BT.601 limited-range integer matrix and a 2x2 chroma average.  This plays the
+    encoder + decoder for tests and benchmarks; it is not part of the analysed path -- whatever bytes it yields simply ARE
+    the decoded picture whose conversion to BGR (cv2.VideoCapture.retrieve, video.py:32) the device reproduces."""
+    b, g, r = (bgr[..., i].astype(np.int32) for i in range(3))
+    y = ((66 * r + 129 * g + 25 * b + 128) >> 8) + 16
+    u = ((-38 * r - 74 * g + 112 * b + 128) >> 8) + 128
+    v = ((112 * r - 94 * g - 18 * b + 128) >> 8) + 128
+    H, W = y.shape
+    sub = lambda p: ((p[0::2, 0::2] + p[0::2, 1::2] + p[1::2, 0::2] + p[1::2, 1::2] + 2) >> 2)
+    out = np.empty(H * W * 3 // 2, np.uint8)
+    out[:H * W] = np.clip(y, 0, 255).reshape(-1)
+    out[H * W:H * W + H * W // 4] = np.clip(sub(u), 0, 255).reshape(-1)
+    out[H * W + H * W // 4:] = np.clip(sub(v), 0, 255).reshape(-1)
+    return out
+
+
 def audio(seed: int, n_samples: int, kind: str = "speech") -> np.ndarray:
     """Mono 16 kHz test audio as float32 in [-1, 1) (what soundfile hands audio.py:15 of the reference), built from
     int16 PCM with integer arithmetic only, so every machine regenerates the same samples.

@@ -3,15 +3,18 @@
     analyze(path: str, meta: dict) -> {"timeline": [...], "summary": {...}, "timeline_ai": <same list>}
 
 Host decode stays what the reference uses (cv2.VideoCapture: grab every frame, retrieve the sampled ones,
-video.py:11,27-34).  Everything computed per sampled frame runs on the B200 through libavd (engine.py);
+video.py:11,27-34; for 8-bit 4:2:0 streams the same FFmpeg decoder is read before its BGR conversion, decode.py).  Everything computed per sampled frame runs on the B200 through libavd (engine.py);
 the O(samples) scalar tail (video.py:54-83) is float64 host arithmetic restated op for op.
 """
 from __future__ import annotations
 
+import contextlib
+
 import numpy as np
 
+from . import decode
 from ._lib import REC_DTYPE, REC_HAS_FLOW, REC_HAS_PREV
-from .engine import default_engine
+from .engine import lease
 
 #: sampled frames per host->device run when decoding a file (bounds pinned memory; one-sample halo between runs)
 DECODE_RUN = 48
@@ -69,8 +72,8 @@ def result_from_records(recs: np.ndarray, H: int, W: int, fps: float, duration: 
 
 def records_from_frames(frames, engine=None) -> np.ndarray:
     """Per-sample records of already-sampled frames (host arrays), through the streaming host entry point."""
-    eng = engine or default_engine()
-    return eng.analyze_host(frames)
+    with lease(engine) as eng:
+        return eng.analyze_host(frames)
 
 
 def analyze_frames(frames, meta: dict, engine=None) -> dict:
@@ -90,8 +93,75 @@ def analyze_frames(frames, meta: dict, engine=None) -> dict:
     return result_from_records(recs, H, W, fps, duration, w=meta.get("width") or W, h=meta.get("height") or H)
 
 
+class _RunPipeline:
+    """Decode of run k+1 overlaps the device work of run k (the reference's loop is strictly serial, video.py:27-58).
+
+    Two pinned stages of DECODE_RUN + 1 frame slots (slot 0 = the one-sample halo: the last frame of the previous run,
+    which seeds the hash / thumbnail chain, video.py:20,26,41,49).  The decode loop fills one stage while a worker thread
+    has the other one inside `Engine.analyze_host` (ctypes releases the GIL; so do cv2 and libav while decoding).
+    """
+
+    def __init__(self, eng, stages, frame_nbytes: int, fmt: str, shape):
+        from concurrent.futures import ThreadPoolExecutor
+        self.eng, self.fmt, self.shape, self.nb = eng, fmt, shape, frame_nbytes
+        self.stages = [st[:(DECODE_RUN + 1) * frame_nbytes].reshape(DECODE_RUN + 1, frame_nbytes) for st in stages]
+        self.cur, self.fill, self.have_halo = 0, 0, False
+        self.pending = [None, None]                          # future of the run that last used stage i
+        self.runs = []
+        self.pool = ThreadPoolExecutor(max_workers=1, thread_name_prefix="avd-run")
+
+    def slot(self) -> np.ndarray:
+        """The staging slot the next sampled frame is decoded into."""
+        return self.stages[self.cur][1 + self.fill]
+
+    def pushed(self):
+        self.fill += 1
+        if self.fill == DECODE_RUN:
+            self.flush()
+
+    def _frames(self, stage, lo, hi):
+        if self.fmt == "bgr":
+            H, W = self.shape
+            return [stage[i].reshape(H, W, 3) for i in range(lo, hi)]
+        return [stage[i] for i in range(lo, hi)]
+
+    def _run(self, stage, lo, hi, drop_first):
+        recs = self.eng.analyze_host(self._frames(stage, lo, hi), fmt=self.fmt, shape=self.shape)
+        return recs[1:] if drop_first else recs
+
+    def flush(self):
+        if self.fill == 0:
+            return
+        stage, other = self.stages[self.cur], self.stages[1 - self.cur]
+        lo = 0 if self.have_halo else 1
+        fut = self.pool.submit(self._run, stage, lo, 1 + self.fill, self.have_halo)
+        self.pending[self.cur] = fut
+        self.runs.append(fut)
+        # the other stage is about to be refilled: its previous run must be done with it, then it gets this run's last
+        # frame as its halo slot
+        if self.pending[1 - self.cur] is not None:
+            self.pending[1 - self.cur].result()
+            self.pending[1 - self.cur] = None
+        np.copyto(other[0], stage[self.fill])
+        self.cur, self.fill, self.have_halo = 1 - self.cur, 0, True
+
+    def finish(self) -> np.ndarray:
+        self.flush()
+        parts = [f.result() for f in self.runs]
+        return np.concatenate(parts) if parts else np.zeros(0, REC_DTYPE)
+
+    def close(self):
+        """Waits for the worker: the stages must not go back to the staging cache while a run still reads them."""
+        self.pool.shutdown(wait=True)
+
+
 def analyze(path: str, meta: dict, engine=None) -> dict:
-    """Same contract as the reference's video.analyze (video.py:10-83)."""
+    """Same contract as the reference's video.analyze (video.py:10-83).
+
+    Decode is the reference's own (cv2.VideoCapture: grab every frame, retrieve the sampled ones).  For 8-bit 4:2:0
+    streams the sampled pictures are taken from the decoder *before* the BGR conversion `retrieve()` does on the host
+    and converted on the device instead, bit for bit (decode.LibavSource, csrc/k0_yuv.cu): half the bytes cross PCIe.
+    """
     import cv2  # host decode only: the reference's own decoder
     cap = cv2.VideoCapture(path)
     if not cap.isOpened():
@@ -101,43 +171,79 @@ def analyze(path: str, meta: dict, engine=None) -> dict:
     h = meta.get("height") or int(cap.get(cv2.CAP_PROP_FRAME_HEIGHT) or 0)
     duration = meta.get("duration") or (cap.get(cv2.CAP_PROP_FRAME_COUNT) / fps if fps > 0 else 0.0)
     step = sample_step(fps)
-    eng = engine or default_engine()
 
-    runs, stage, fill, halo, shape = [], None, 0, None, None
-    index = 0
-
-    def flush():
-        nonlocal fill, halo
-        if fill == 0:
-            return
-        batch = [halo] + [stage[i] for i in range(fill)] if halo is not None else [stage[i] for i in range(fill)]
-        recs = eng.analyze_host(batch)
-        runs.append(recs[1:] if halo is not None else recs)
-        halo = stage[fill - 1].copy()
-        fill = 0
-
-    while True:
-        if not cap.grab():
-            break
-        if index % step == 0:
-            ok, frame = cap.retrieve()
-            if not ok:
-                break                                   # video.py:33: keep what we have
-            if stage is None:
-                shape = frame.shape
-                stage = eng.pinned((DECODE_RUN,) + tuple(shape))
-            if frame.shape != shape:
-                raise ValueError("frame size changed mid-stream")
-            np.copyto(stage[fill], frame)
-            fill += 1
-            if fill == DECODE_RUN:
-                flush()
-        index += 1
-    cap.release()
-    flush()
-    recs = np.concatenate(runs) if runs else np.zeros(0, REC_DTYPE)
-    H, W = (shape[0], shape[1]) if shape else (int(h), int(w))
+    yuv = decode.open_yuv_source(path)
+    if yuv is not None:
+        try:
+            first = yuv.grab()                               # learns the pixel format; may refuse the stream
+        except decode.DecodeUnavailable:
+            yuv.release()
+            yuv = None
+    try:
+        with lease(engine) as eng:
+            if yuv is not None:
+                cap.release()
+                recs, shape = _decode_loop_yuv(eng, yuv, first, step)
+            else:
+                recs, shape = _decode_loop_bgr(eng, cap, step)
+    finally:
+        cap.release()
+        if yuv is not None:
+            yuv.release()
+    H, W = shape if shape else (int(h), int(w))
     return result_from_records(recs, H, W, fps, duration, w=w, h=h)
+
+
+def _decode_loop_bgr(eng, cap, step):
+    pipe, shape, index = None, None, 0
+    with contextlib.ExitStack() as stack:
+        try:
+            while True:
+                if not cap.grab():
+                    break
+                if index % step == 0:
+                    ok, frame = cap.retrieve()
+                    if not ok:
+                        break                                   # video.py:33: keep what we have
+                    if pipe is None:
+                        shape = frame.shape
+                        nb = int(frame.size)
+                        stages = [stack.enter_context(eng.staging((DECODE_RUN + 1) * nb)) for _ in range(2)]
+                        pipe = _RunPipeline(eng, stages, nb, "bgr", (shape[0], shape[1]))
+                    if frame.shape != shape:
+                        raise ValueError("frame size changed mid-stream")
+                    np.copyto(pipe.slot().reshape(shape), frame)
+                    pipe.pushed()
+                index += 1
+            recs = pipe.finish() if pipe else np.zeros(0, REC_DTYPE)
+        finally:
+            if pipe:
+                pipe.close()
+    return recs, (shape[0], shape[1]) if shape else None
+
+
+def _decode_loop_yuv(eng, src, have_first: bool, step):
+    pipe, shape, index = None, None, 0
+    with contextlib.ExitStack() as stack:
+        try:
+            ok = have_first
+            while ok:
+                if index % step == 0:
+                    if pipe is None:
+                        shape = (src.height, src.width)
+                        nb = src.frame_nbytes()
+                        stages = [stack.enter_context(eng.staging((DECODE_RUN + 1) * nb)) for _ in range(2)]
+                        pipe = _RunPipeline(eng, stages, nb, src.fmt, shape)
+                    if not src.retrieve_into(pipe.slot()):
+                        break
+                    pipe.pushed()
+                index += 1
+                ok = src.grab()
+            recs = pipe.finish() if pipe else np.zeros(0, REC_DTYPE)
+        finally:
+            if pipe:
+                pipe.close()
+    return recs, shape
 
 
 def analyze_frames_batch(clips, metas, engine=None):
@@ -146,12 +252,11 @@ def analyze_frames_batch(clips, metas, engine=None):
     records at clip boundaries are then detached from their (foreign) predecessor, which is exactly the state
     video.py starts every clip with (prev_hash = None, prev_frame_small = None; video.py:20,26).
     Returns one result dict per clip."""
-    eng = engine or default_engine()
     frames, starts = [], []
     for c in clips:
         starts.append(len(frames))
         frames.extend(c[i] for i in range(len(c)))
-    recs = eng.analyze_host(frames) if frames else np.zeros(0, REC_DTYPE)
+    recs = records_from_frames(frames, engine) if frames else np.zeros(0, REC_DTYPE)
     out = []
     for ci, c in enumerate(clips):
         n = len(c)

@@ -62,9 +62,11 @@ void avd_destroy(avd_ctx *ctx);
 const char *avd_last_error(const avd_ctx *ctx);
 int  avd_sync(avd_ctx *ctx);                         /* waits for all work of the context */
 
-/* pinned host memory for frame batches (cudaHostAlloc) */
+/* pinned host memory for frame batches (cudaHostAlloc).  Regions still allocated when the context is destroyed
+ * are released by avd_destroy; avd_host_alloc_count is the number of live regions (leak checks). */
 void *avd_host_alloc(avd_ctx *ctx, size_t bytes);
 void  avd_host_free(avd_ctx *ctx, void *p);
+size_t avd_host_alloc_count(const avd_ctx *ctx);
 
 /*
  * K1 -- per-frame features of n BGR frames resident in HBM.   Replaces, per frame:
@@ -110,6 +112,22 @@ int avd_gray(avd_ctx *ctx, const uint8_t *d_bgr, int H, int W, size_t row_pitch,
  */
 int avd_analyze_host(avd_ctx *ctx, const uint8_t *const *h_frames, int n, int H, int W, size_t row_pitch,
                      avd_sample_rec *h_rec);
+
+/*
+ * Decode -> device, first step: the decoder's own planar 4:2:0 pictures cross PCIe (1.5 bytes
+ * per pixel instead of 3) and the colour conversion cv2.VideoCapture.retrieve() performs on the host (video.py:32;
+ * sws_scale yuv420p/yuvj420p -> bgr24, unscaled) runs on the device, bit for bit: libswscale's 16-bit fixed-point
+ * yuv2rgb arithmetic with the ITU-601 default coefficients, chroma replicated 2x2.  A frame is dense I420:
+ * H rows of W luma bytes, then (H/2) x (W/2) U, then (H/2) x (W/2) V; W and H even.  full_range = 1 for yuvj420p (MJPEG).
+ *
+ * avd_yuv420_to_bgr: n device-resident frames (frame i at d_yuv + i*yuv_frame_stride) -> packed BGR frames.
+ * avd_analyze_host_yuv420: avd_analyze_host for 4:2:0 host frames; records equal those of avd_analyze_host on the BGR
+ * frames the reference's decoder would have produced from the same pictures.
+ */
+int avd_yuv420_to_bgr(avd_ctx *ctx, const uint8_t *d_yuv, size_t yuv_frame_stride, int n, int H, int W, int full_range,
+                      uint8_t *d_bgr, size_t row_pitch, size_t frame_stride, void *stream);
+int avd_analyze_host_yuv420(avd_ctx *ctx, const uint8_t *const *h_frames, int n, int H, int W, int full_range,
+                            avd_sample_rec *h_rec);
 
 /*
  * K3 -- the per-clip scoring tail on the device, for batches of clips whose records are already in HBM (SURVEY.md
@@ -174,6 +192,11 @@ int avd_audio_windows(avd_ctx *ctx, const float *h_wav, long long n_samples, int
 
 /* Counters for bench.py: number of kernel launches issued by this context since creation. */
 uint64_t avd_launch_count(const avd_ctx *ctx);
+
+/* The library's scratch buffers (tables, Farneback workspace, fix-up lists) only ever grow; when one has to move, this
+ * counter is bumped.  A caller that captured device-pointer entry points into a CUDA graph must re-capture when the
+ * value differs from the one it saw at capture time (the graph holds the old addresses). */
+uint64_t avd_ws_generation(const avd_ctx *ctx);
 
 /* Per-kernel device timing for bench.py: when enabled, every launch is bracketed by CUDA events on its
  * stream.  avd_profile_read synchronises, writes JSON {"kernel": {"ms": total, "launches": n}, ...} to buf

@@ -14,11 +14,14 @@ import numpy as np
 class SampleChain:
     """Carried state of the sampled-frame loop: previous hash and previous 320x320 gray (video.py:20,26)."""
 
-    def __init__(self):
+    def __init__(self, collect_ints: bool = False):
         self.prev_hash = None
         self.prev_small = None
         self.dup = 0
         self.flow_means, self.flow_vars, self.textures, self.timeline = [], [], [], []
+        # parity passes only (never the timed baseline): the integer intermediates behind the floats above
+        self.collect_ints = collect_ints
+        self.hash_words, self.hams, self.lap_sums = [], [], []
 
     def push(self, frame: np.ndarray, emit: bool = True):
         import cv2
@@ -26,6 +29,9 @@ class SampleChain:
         hsh = (g32 >= g32.mean()).astype(np.uint8).flatten()                                                # :7-8
         if emit and self.prev_hash is not None and int(np.sum(hsh ^ self.prev_hash)) == 0:                 # :37-40
             self.dup += 1
+        if emit and self.collect_ints:
+            self.hash_words.append(np.packbits(hsh, bitorder="little").view(np.uint32).copy())
+            self.hams.append(int(np.sum(hsh ^ self.prev_hash)) if self.prev_hash is not None else -1)
         self.prev_hash = hsh
         small = cv2.resize(cv2.cvtColor(frame, cv2.COLOR_BGR2GRAY), (320, 320))                             # :43
         if emit and self.prev_small is not None:
@@ -36,23 +42,28 @@ class SampleChain:
         self.prev_small = small
         if not emit:
             return
-        tex = float(cv2.Laplacian(cv2.cvtColor(frame, cv2.COLOR_BGR2GRAY), cv2.CV_64F).var())               # :51-52
+        lap = cv2.Laplacian(cv2.cvtColor(frame, cv2.COLOR_BGR2GRAY), cv2.CV_64F)                            # :51
+        tex = float(lap.var())                                                                              # :52
         self.textures.append(tex)
+        if self.collect_ints:
+            self.lap_sums.append((int(lap.sum()), int((lap * lap).sum())))
         mot = self.flow_means[-1] if self.flow_means else 0.0
         self.timeline.append(float(np.clip(1.0 - (tex / (tex + 1000.0)) * (1.0 + mot), 0.0, 1.0)))          # :56-57
 
 
-def run_chunk(frames, halo=None):
+def run_chunk(frames, halo=None, collect_ints: bool = False):
     """Body over a contiguous chunk of sampled frames (optionally seeded by a halo frame).  Returns
-    (textures, flow_means, flow_vars, dup, timeline)."""
+    (textures, flow_means, flow_vars, dup, timeline); with collect_ints (parity passes, untimed) additionally
+    (hash words per sample, Hamming to the predecessor or -1, (sum, sum of squares) of the Laplacian)."""
     import cv2
     cv2.setNumThreads(1)
-    ch = SampleChain()
+    ch = SampleChain(collect_ints)
     if halo is not None:
         ch.push(halo, emit=False)
     for f in frames:
         ch.push(f)
-    return ch.textures, ch.flow_means, ch.flow_vars, ch.dup, ch.timeline
+    out = (ch.textures, ch.flow_means, ch.flow_vars, ch.dup, ch.timeline)
+    return out + (ch.hash_words, ch.hams, ch.lap_sums) if collect_ints else out
 
 
 _SHARED = {}
@@ -61,7 +72,7 @@ _SHARED = {}
 def _worker(args):
     lo, hi = args
     fr = _SHARED["frames"]
-    return run_chunk(fr[lo:hi], fr[lo - 1] if lo > 0 else None)
+    return run_chunk(fr[lo:hi], fr[lo - 1] if lo > 0 else None, _SHARED.get("collect_ints", False))
 
 
 def run_parallel(frames, procs: int):
@@ -103,7 +114,15 @@ class Pool:
 
     def step(self):
         parts = self.pool.map(_worker, self.bounds) if self.pool else [_worker(self.bounds[0])]
+        self.last = parts                       # per-chunk outputs of this pass (bench.py's parity check reads them)
         return sum(len(p[0]) for p in parts)
+
+    def outputs(self):
+        """The last pass, concatenated in sample order: dict of textures, flow_means, flow_vars, dup, timeline.  Every chunk
+        after the first was seeded by its halo sample, so flow lists have one entry per sample except the very first."""
+        parts = self.last
+        cat = lambda k: [x for p in parts for x in p[k]]
+        return {"textures": cat(0), "flow_means": cat(1), "flow_vars": cat(2), "dup": sum(p[3] for p in parts), "timeline": cat(4)}
 
     def close(self):
         if self.pool:

@@ -1,0 +1,245 @@
+"""GPU tests added in round 2 (pytest -m gpu): the decode -> device seam (4:2:0 upload + on-device colour conversion),
+the full-size configs[1] golden, and the engine's resource handling (staging reuse, graph invalidation, engine pool).
+Everything goes through the C ABI; the checkers are the CPU oracles and the fixtures made from the reference's own code."""
+import copy
+import hashlib
+import json
+import os
+import threading
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, close, flow_atol, summary_flow_atol
+
+pytestmark = pytest.mark.gpu
+
+
+def sha(a):
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+@pytest.fixture(scope="module")
+def torch():
+    import torch as t
+    assert t.cuda.is_available(), "these tests need a GPU"
+    return t
+
+
+@pytest.fixture(scope="module")
+def eng(torch):
+    from avd_b200.engine import Engine
+    e = Engine(0)
+    yield e
+    e.close()
+
+
+def _i420(rng, H, W):
+    return rng.integers(0, 256, H * W * 3 // 2, dtype=np.uint8)
+
+
+@pytest.mark.parametrize("H,W", [(1080, 1920), (720, 1280), (480, 854), (34, 66), (2160, 3840)])
+@pytest.mark.parametrize("full", [False, True])
+def test_k0_colour_conversion_equals_swscale_oracle(torch, eng, H, W, full):
+    """csrc/k0_yuv.cu against the restatement of libswscale's yuv420p -> bgr24 (itself pinned to the library): random
+    planes, vector kernel (W % 16 == 0) and byte kernel (854, 66), limited and full range, dense and padded BGR pitch."""
+    from oracle import yuv_oracle as YO
+    rng = np.random.default_rng([H, W, int(full)])
+    n = 2
+    yuv = np.stack([_i420(rng, H, W) for _ in range(n)])
+    want = np.stack([YO.i420_to_bgr(f, H, W, full) for f in yuv])
+    for pad in (0, 16 - (3 * W) % 16 if (3 * W) % 16 else 32):
+        got = eng.yuv420_to_bgr(torch.from_numpy(yuv).cuda(), H, W, full, pitch=3 * W + pad)
+        assert np.array_equal(got.cpu().numpy()[:, :, :3 * W].reshape(n, H, W, 3), want), (H, W, full, pad)
+
+
+def test_yuv_cube_on_device(torch, eng, ):
+    """Every (Y, U, V) triple through the device kernel equals the oracle (both ranges)."""
+    from oracle import yuv_oracle as YO
+    U, V = np.meshgrid(np.arange(256, dtype=np.uint8), np.arange(256, dtype=np.uint8), indexing="ij")
+    for full in (False, True):
+        frames, want = [], []
+        for y0 in range(64):
+            Y = np.empty((512, 512), np.uint8)
+            Y[0::2, 0::2], Y[0::2, 1::2], Y[1::2, 0::2], Y[1::2, 1::2] = y0, (y0 + 64) & 255, (y0 + 128) & 255, (y0 + 192) & 255
+            frames.append(np.concatenate([Y.reshape(-1), U.reshape(-1), V.reshape(-1)]))
+            want.append(YO.yuv420_to_bgr(Y, U, V, full))
+        got = eng.yuv420_to_bgr(torch.from_numpy(np.stack(frames)).cuda(), 512, 512, full).cpu().numpy().reshape(64, 512, 512, 3)
+        assert np.array_equal(got, np.stack(want)), full
+
+
+@pytest.mark.parametrize("H,W,fmt", [(720, 1280, "i420"), (360, 640, "j420"), (480, 854, "i420")])
+def test_host_yuv_path_equals_host_bgr_path(synth, eng, H, W, fmt):
+    """avd_analyze_host_yuv420 on the decoder's pictures == avd_analyze_host on the BGR frames cv2 would have made of
+    them: records byte for byte (same K1 / K2 downstream of the conversion)."""
+    from oracle import yuv_oracle as YO
+    clip = synth.Clip(60, H, W, seed=41, events=True, pan=2)
+    bgr0 = [clip[i] for i in range(0, 60, 3)]                       # 20 samples
+    Hc, Wc = H & ~1, W & ~1
+    yuv = [synth.bgr_to_i420(f[:Hc, :Wc]) for f in bgr0]               # "decoder output"
+    bgr = [YO.i420_to_bgr(f, Hc, Wc, fmt == "j420") for f in yuv]   # what cv2.VideoCapture.retrieve() returns for it
+    a = eng.analyze_host(yuv, fmt=fmt, shape=(Hc, Wc))
+    b = eng.analyze_host(bgr)
+    assert a.tobytes() == b.tobytes()
+    assert (a["flags"][1:] & 2).all()
+
+
+def _write_clip(cv2, path, fourcc, synth, n, H, W, seed, fps=30.0):
+    vw = cv2.VideoWriter(path, cv2.VideoWriter_fourcc(*fourcc), fps, (W, H))
+    if not vw.isOpened():
+        return False
+    clip = synth.Clip(n, H, W, seed, events=True, pan=2)
+    for i in range(n):
+        vw.write(clip[i])
+    vw.release()
+    return True
+
+
+@pytest.mark.parametrize("fourcc,ext", [("mp4v", "mp4"), ("MJPG", "avi")])
+def test_analyze_path_yuv_route_equals_cv2_route_and_reference_body(tmp_path, synth, eng, monkeypatch, fourcc, ext):
+    """video.analyze(path) on a real lossy file: the 4:2:0 route (libav pictures -> device conversion) returns exactly
+    the dict of the cv2.VideoCapture route, and both agree with the reference's own cv2/NumPy body on the frames
+    cv2.VideoCapture decodes.  meta fps = 2 -> step 1 -> 110 samples = three overlapped runs with halos."""
+    cv2 = pytest.importorskip("cv2")
+    from avd_b200 import decode, video
+    from oracle import cv_body
+    path = str(tmp_path / f"c.{ext}")
+    if not _write_clip(cv2, path, fourcc, synth, 110, 240, 320, 51):
+        pytest.skip(f"no {fourcc} encoder")
+    meta = {"fps": 2.0, "width": 320, "height": 240, "duration": 55.0}
+    monkeypatch.setenv("AVD_DECODE", "cv2")
+    via_cv2 = video.analyze(path, dict(meta), engine=eng)
+    monkeypatch.setenv("AVD_DECODE", "auto")
+    src = decode.open_yuv_source(path)
+    if src is None:
+        pytest.skip("libav shim unavailable")
+    src.release()
+    via_yuv = video.analyze(path, dict(meta), engine=eng)
+    assert via_yuv == via_cv2
+    cap, frames = cv2.VideoCapture(path), []
+    while True:
+        ok, f = cap.read()
+        if not ok:
+            break
+        frames.append(f)
+    tex, fm, fv, dup, tl = cv_body.run_chunk(frames)
+    assert len(via_yuv["timeline"]) == 55 and len(tl) == 110
+    for a, b in zip(via_yuv["timeline"], tl[:55]):
+        assert close(a, b, atol=5e-5)
+    assert via_yuv["summary"]["dup_density"] == dup / 109
+    assert close(via_yuv["summary"]["flow_mean"], float(np.mean(fm)), atol=summary_flow_atol(fm, "flow_mean"))
+    assert close(via_yuv["summary"]["texture_var"], float(np.var(tex)), rtol=1e-9)
+
+
+def test_full_1080p_clip_vs_reference_golden(synth, eng):
+    """BASELINE configs[1], the WHOLE clip: 120 samples of the 1080p seed-1 clip against what the unmodified reference
+    produced (tests/golden/golden_1080p_full.json): integer fields exact for every sample, flow statistics for all 119
+    pairs, the returned dict, and fuse()'s verdict."""
+    from avd_b200 import fusion, hints, video
+    with open(os.path.join(ROOT, "tests", "golden", "golden_1080p_full.json")) as f:
+        g = json.load(f)
+    clip = synth.Clip(g["n_frames"], g["H"], g["W"], g["seed"], fps=g["fps"])
+    frames = clip.sampled(g["step"])
+    assert sha(frames[:8]) == g["input_sha_first8"]
+    recs = eng.analyze_host(frames)
+    assert len(recs) == 120
+    assert [r["hash"].tolist() for r in recs] == g["hash_words"]
+    assert [int(x) for x in recs["ham_prev"][1:]] == g["ham"]
+    assert [int(x) for x in recs["lap_sum"]] == g["lap_sum"] and [int(x) for x in recs["lap_sumsq"]] == g["lap_sumsq"]
+    worst = 0.0
+    for r, (m, v) in zip(recs[1:], g["flow_stats"]):
+        assert close(float(r["flow_mean"]), m, atol=flow_atol(m)), (float(r["flow_mean"]), m)
+        assert close(float(r["flow_var"]), v, atol=flow_atol(m)), (float(r["flow_var"]), v)
+        if m >= 1e-2:
+            worst = max(worst, abs(float(r["flow_mean"]) - m) / m)
+    assert worst <= 1e-4
+    out = video.result_from_records(recs, g["H"], g["W"], g["fps"], g["meta"]["duration"], w=g["W"], h=g["H"])
+    ref = g["result"]
+    assert len(out["timeline"]) == len(ref["timeline"]) == 60
+    for a, b in zip(out["timeline"], ref["timeline"]):
+        assert close(a, b)
+    means = [m for m, _ in g["flow_stats"]]
+    for k, b in ref["summary"].items():
+        a = out["summary"][k]
+        if k in ("w", "h", "dup_density", "scene_change_rate", "fps"):
+            assert a == b, k
+        else:
+            assert close(a, b, atol=summary_flow_atol(means, k)), (k, a, b)
+    assert hints.compute_hints(dict(g["hints_meta"]), "") == g["hints"]
+    fused = fusion.fuse(fusion.neutral_audio(60), copy.deepcopy(out), g["hints"], with_raw=True)
+    want = g["fused_with_neutral_audio"]
+    assert fused["result"]["label"] == want["result"]["label"] and fused["peaks"] == want["peaks"]
+    assert abs(fused["_raw_score"] - float(np.mean(want["timeline_binned"]))) <= 0.05   # sanity: same scale
+    assert abs(fused["result"]["ai_score"] - want["result"]["ai_score"]) <= 0.01 + 1e-9
+    for a, b in zip(fused["timeline_binned"], want["timeline_binned"]):
+        assert abs(a - b) <= 1e-3
+
+
+def test_analyze_path_reuses_pinned_staging(tmp_path, synth, eng):
+    """video.analyze must not allocate pinned memory per call.  Ten calls: the number of live
+    cudaHostAlloc regions stops growing after the first."""
+    cv2 = pytest.importorskip("cv2")
+    from avd_b200 import video
+    path = str(tmp_path / "c.avi")
+    if not _write_clip(cv2, path, "MJPG", synth, 40, 240, 320, 61):
+        pytest.skip("no MJPG encoder")
+    meta = {"fps": 30.0, "width": 320, "height": 240, "duration": 40 / 30}
+    first = video.analyze(path, dict(meta), engine=eng)
+    n0 = eng.pinned_regions
+    assert n0 >= 2
+    for _ in range(9):
+        assert video.analyze(path, dict(meta), engine=eng) == first
+    assert eng.pinned_regions == n0
+    a = eng.pinned((1024,))
+    assert eng.pinned_regions == n0 + 1
+    eng.free_pinned(a)
+    assert eng.pinned_regions == n0
+
+
+def test_cached_graph_is_recaptured_after_workspace_growth(synth, torch):
+    """a cached CUDA graph holds the addresses of the library's grow-only scratch buffers; a later,
+    larger call moves them.  The engine must notice (avd_ws_generation) and re-capture instead of replaying."""
+    from avd_b200.engine import Engine
+    e = Engine(0)
+    try:
+        clip = synth.Clip(64, 360, 640, seed=71, events=True)
+        small = torch.from_numpy(np.stack([clip[i] for i in range(0, 16, 2)])).cuda()
+        big = torch.from_numpy(np.stack([clip[i] for i in range(64)])).cuda()
+        want = e.analyze_device(small).cpu().numpy().tobytes()
+        assert e.analyze_device_graph(small).cpu().numpy().tobytes() == want
+        gen = e.ws_generation
+        e.analyze_device(big)                                   # grows the Farneback workspace, thumbnails' scratch, ...
+        assert e.ws_generation > gen
+        assert e.analyze_device_graph(small).cpu().numpy().tobytes() == want
+        assert e.analyze_device_graph(small).cpu().numpy().tobytes() == want
+        for k in range(12):                                     # the cache is bounded
+            e.analyze_device_graph(small[:k % 4 + 2].clone())
+        assert len(e._graphs) <= e.GRAPH_CACHE
+    finally:
+        e.close()
+
+
+def test_engine_pool_serves_concurrent_requests(synth):
+    """Requests on pool threads (api.py:133) lease separate contexts: every caller gets the dict it would get alone."""
+    from avd_b200 import video
+    from avd_b200.engine import Engine, engine_pool
+    clips = [synth.Clip(60, 360, 640, seed=130 + i, fps=30.0) for i in range(8)]
+    reqs = [(list(c.sampled(15)), {"fps": 30.0, "width": 640, "height": 360, "duration": 2.0}) for c in clips]
+    solo = Engine(0)
+    want = [video.analyze_frames(f, m, engine=solo) for f, m in reqs]
+    solo.close()
+    got, errs, gate = [None] * 8, [], threading.Barrier(8)
+
+    def work(i):
+        try:
+            gate.wait()
+            for _ in range(4):
+                got[i] = video.analyze_frames(*reqs[i])         # engine=None: leased from the device's pool
+        except Exception as e:                                  # pragma: no cover
+            errs.append(e)
+
+    ts = [threading.Thread(target=work, args=(i,)) for i in range(8)]
+    [t.start() for t in ts]
+    [t.join() for t in ts]
+    assert not errs and got == want
+    assert 1 <= len(engine_pool(0)._all) <= engine_pool(0).size
