@@ -289,15 +289,16 @@ int avd_shape_plan(int H, int W, avd_shape_plan_t *out)
     }
     for (int s = 0; s < 256; s++) { out->strip_tx0[s] = t.strip_tx0[s]; out->strip_ntx[s] = t.strip_ntx[s]; }
     for (int r = 0; r < H && r < 4096; r++) out->rowinfo[r] = t.rowinfo[r];
-    // which per-frame kernel a dense, 16-byte aligned buffer of this shape gets (0 streaming, 2 banded, 1 generic)
+    // which per-frame kernel a dense, 16-byte aligned buffer of this shape gets (0 streaming, 2 banded, 3 any-width fused, 1 generic)
     const size_t pitch = (size_t)W * 3;
-    out->k1_path = k1_fused_supported(H, W, pitch, pitch * H, nullptr, &t) ? 0 : (k1_banded_supported(H, W, pitch, pitch * H, nullptr) ? 2 : 1);
+    out->k1_path = k1_fused_supported(H, W, pitch, pitch * H, nullptr, &t) ? 0 :
+                   (k1_banded_supported(H, W, pitch, pitch * H, nullptr) ? 2 : (k1_rows_supported(H, W, &t) ? 3 : 1));
     return AVD_OK;
 }
 
 int avd_set_k1_mode(avd_ctx *ctx, int mode)
 {
-    if (!ctx || mode < 0 || mode > 2) return AVD_ERR_ARG;
+    if (!ctx || mode < 0 || mode > 3) return AVD_ERR_ARG;
     ctx->k1_mode = mode;
     return AVD_OK;
 }
@@ -340,6 +341,8 @@ int avd_frames_features(avd_ctx *ctx, const uint8_t *d_bgr, int n, int H, int W,
         rc = k1_fused(ctx, d_bgr, n, H, W, row_pitch, frame_stride, tab, htab, d_rec, d_thumbs, d_area32, ctx->fixlist, st);
     else if ((ctx->k1_mode == 0 || ctx->k1_mode == 2) && k1_banded_supported(H, W, row_pitch, frame_stride, d_bgr))
         rc = k1_banded(ctx, d_bgr, n, H, W, row_pitch, frame_stride, tab, htab, d_rec, d_thumbs, d_area32, st);
+    else if (ctx->k1_mode != 1 && k1_rows_supported(H, W, htab))
+        rc = k1_rows(ctx, d_bgr, n, H, W, row_pitch, frame_stride, tab, htab, d_rec, d_thumbs, d_area32, st);
     else
         rc = k1_generic(ctx, d_bgr, n, H, W, row_pitch, frame_stride, tab, htab, d_rec, d_thumbs, d_area32, st);
     if (rc) return rc;

@@ -139,6 +139,11 @@ int k1_fused(avd_ctx *ctx, const uint8_t *d_bgr, int n, int H, int W, size_t pit
 // k0_yuv.cu: dense I420 frames (Y HxW, U, V (H/2)x(W/2)) -> packed BGR, swscale's unscaled yuv420p->bgr24 arithmetic
 int k0_yuv420_to_bgr(avd_ctx *ctx, const uint8_t *d_yuv, size_t yuv_stride, int n, int H, int W, bool full_range,
                      uint8_t *d_bgr, size_t pitch, size_t fstride, cudaStream_t st);
+// k1_rows.cu (any width / alignment; the band's gray rows in shared memory)
+bool k1_rows_supported(int H, int W, const ShapeTables *htab);
+int k1_rows(avd_ctx *ctx, const uint8_t *d_bgr, int n, int H, int W, size_t pitch, size_t fstride,
+            const ShapeTables *tab, const ShapeTables *htab, avd_sample_rec *d_rec, uint8_t *d_thumbs,
+            uint8_t *d_area32, cudaStream_t st);
 // k2_flow.cu
 int k2_reserve(avd_ctx *ctx, int n_pairs);   // size the workspace for runs of up to n_pairs pairs now
 int k2_flow(avd_ctx *ctx, const uint8_t *d_prev, const uint8_t *d_next, size_t prev_stride, size_t next_stride,

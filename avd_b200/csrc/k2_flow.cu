@@ -7,12 +7,14 @@
 // B200 design: the batch dimension is the image / pair index.  The per-IMAGE work (pyramid + polynomial
 // expansion) is done once per thumbnail, not once per pair as the CPU library does (each thumbnail is
 // "next" of one pair and "prev" of the following one).  All intermediates are planar float32 so every
-// warp access is a contiguous 128-byte line; they are sized to stay L2-resident per batch.
+// warp access is a contiguous 128-byte line.  At the finest level they are NOT L2-resident for a 119-pair batch (M alone is
+// 244 MB against 126 MB of L2): measured DRAM traffic per kernel is in profiles/r02_k2_notes.md.
 // Compiled with -fmad=false: the float sequences round exactly like the scalar library code.
 #include "avd_internal.h"
 #include <math.h>
 #include <stdlib.h>
 #include <stdio.h>
+#include <string.h>
 
 namespace {
 
@@ -201,20 +203,33 @@ __device__ __forceinline__ float up2_sample(const float *__restrict__ c, int cs,
     return (r0 * ay0 + r1 * fy) * 2.f;
 }
 
+// ---- 15x15 box sums (float64) + 2x2 solve -------------------------------------------------------------------
+// Strip geometry shared by the kernel and the host: a warp covers 128 columns (4 per lane); lanes 2..29 produce the 112
+// output columns, lanes 0,1,30,31 are the 8-column halo (>= 7) on each side.
+constexpr int BX_COLS = 112, BS_M = 7;
+constexpr int BX_MIN_SEG = 8;
+__host__ __device__ constexpr int bx_strips(int s) { return (s + BX_COLS - 1) / BX_COLS; }
+__host__ __device__ constexpr int bx_segs(int s, int seg) { return (s + seg - 1) / seg; }
+
+// ---- update matrices ---------------------------------------------------------------------------------
 // The five entries of the update matrix of one pixel (the library's FarnebackUpdateMatrices) for the
-// displacement (dx, dy): bilinear warp of R1, border scaling.  
-__device__ __forceinline__ void um_pixel(const float *__restrict__ R0, const float *__restrict__ R1, int s, int x, int y, float dx, float dy, float *m)
+// displacement (dx, dy): bilinear warp of R1, border scaling.  The level's size is a compile-time constant: every plane /
+// row offset is an immediate of the load instruction instead of 64-bit integer arithmetic (round 1's runtime-level kernel
+// spent ~40 % of its issue slots on addresses: 226 -> 167 lane-instructions per pixel).
+template <int S>
+__device__ __forceinline__ void um_pixel_c(const float *__restrict__ R0, const float *__restrict__ R1, int x, int y, float dx, float dy, float *m)
 {
-    const size_t plane = (size_t)s * s, o = (size_t)y * s + x;
+    constexpr int plane = S * S;
+    const int o = y * S + x;
     float fx = (float)x + dx, fy = (float)y + dy;
     int x1 = (int)floorf(fx), y1 = (int)floorf(fy);
     fx -= (float)x1; fy -= (float)y1;
     float r2, r3, r4, r5, r6;
-    float q0 = R0[o], q1 = R0[plane + o], q2 = R0[2 * plane + o], q3 = R0[3 * plane + o], q4 = R0[4 * plane + o];
-    if ((unsigned)x1 < (unsigned)(s - 1) && (unsigned)y1 < (unsigned)(s - 1)) {
-        float a00 = (1.f - fx) * (1.f - fy), a01 = fx * (1.f - fy), a10 = (1.f - fx) * fy, a11 = fx * fy;
-        size_t b = (size_t)y1 * s + x1;
-#define BIL(c) (((a00 * R1[(c) * plane + b] + a01 * R1[(c) * plane + b + 1]) + a10 * R1[(c) * plane + b + s]) + a11 * R1[(c) * plane + b + s + 1])
+    const float q0 = R0[o], q1 = R0[plane + o], q2 = R0[2 * plane + o], q3 = R0[3 * plane + o], q4 = R0[4 * plane + o];
+    if ((unsigned)x1 < (unsigned)(S - 1) && (unsigned)y1 < (unsigned)(S - 1)) {
+        const float a00 = (1.f - fx) * (1.f - fy), a01 = fx * (1.f - fy), a10 = (1.f - fx) * fy, a11 = fx * fy;
+        const float *b = R1 + (y1 * S + x1);
+#define BIL(c) (((a00 * b[(c) * plane] + a01 * b[(c) * plane + 1]) + a10 * b[(c) * plane + S]) + a11 * b[(c) * plane + S + 1])
         r2 = BIL(0); r3 = BIL(1); r4 = BIL(2); r5 = BIL(3); r6 = BIL(4);
 #undef BIL
         r4 = (q2 + r4) * 0.5f; r5 = (q3 + r5) * 0.5f; r6 = (q4 + r6) * 0.25f;
@@ -225,11 +240,11 @@ __device__ __forceinline__ void um_pixel(const float *__restrict__ R0, const flo
     r3 = (q1 - r3) * 0.5f;
     r2 = r2 + (r4 * dy + r6 * dx);
     r3 = r3 + (r6 * dy + r5 * dx);
-    const int B = 5;
-    if ((unsigned)(x - B) >= (unsigned)(s - 2 * B) || (unsigned)(y - B) >= (unsigned)(s - 2 * B)) {
+    constexpr int B = 5;
+    if ((unsigned)(x - B) >= (unsigned)(S - 2 * B) || (unsigned)(y - B) >= (unsigned)(S - 2 * B)) {
         const float border[5] = {0.14f, 0.14f, 0.4472f, 0.4472f, 0.4472f};
-        float sc = (x < B ? border[x] : 1.f) * (x >= s - B ? border[s - x - 1] : 1.f) *
-                   (y < B ? border[y] : 1.f) * (y >= s - B ? border[s - y - 1] : 1.f);
+        const float sc = (x < B ? border[x] : 1.f) * (x >= S - B ? border[S - x - 1] : 1.f) *
+                         (y < B ? border[y] : 1.f) * (y >= S - B ? border[S - y - 1] : 1.f);
         r2 *= sc; r3 *= sc; r4 *= sc; r5 *= sc; r6 *= sc;
     }
     m[0] = r4 * r4 + r6 * r6;
@@ -239,275 +254,136 @@ __device__ __forceinline__ void um_pixel(const float *__restrict__ R0, const flo
     m[4] = r6 * r2 + r5 * r3;
 }
 
-template <int FLOWSRC>
-__global__ void __launch_bounds__(256) update_matrices_kernel(const float *__restrict__ Rall, const float *__restrict__ flow,
-                                                              const float *__restrict__ coarse, float *__restrict__ Mall,
-                                                              float *__restrict__ flow_store, int k, int pair_img_mode, int p_base)
+template <int K, int FLOWSRC>
+__global__ void __launch_bounds__(256) um_kernel(const float *__restrict__ Rall, const float *__restrict__ flow, const float *__restrict__ coarse,
+                                                 float *__restrict__ Mall, int pair_img_mode, int p_base)
 {
-    const int s = lvl_size(k);
-    int x = blockIdx.x * 32 + threadIdx.x, y = blockIdx.y * 8 + threadIdx.y, p = blockIdx.z + p_base;
-    if (x >= s || y >= s) return;
-    int ia = pair_img_mode == 2 ? 2 * p : p, ib = ia + 1;
-    size_t plane = (size_t)s * s, o = (size_t)y * s + x;
-    const float *R0 = Rall + (size_t)ia * PYR_PX * 5 + (size_t)lvl_off(k) * 5;
-    const float *R1 = Rall + (size_t)ib * PYR_PX * 5 + (size_t)lvl_off(k) * 5;
+    constexpr int S = lvl_size(K), plane = S * S;
+    const int x = blockIdx.x * 32 + threadIdx.x, y = blockIdx.y * 8 + threadIdx.y, p = blockIdx.z + p_base;
+    if (x >= S || y >= S) return;
+    const int ia = pair_img_mode == 2 ? 2 * p : p;
+    const int o = y * S + x;
+    const float *R0 = Rall + (size_t)ia * PYR_PX * 5 + lvl_off(K) * 5;
+    const float *R1 = R0 + (size_t)PYR_PX * 5;
     float dx = 0.f, dy = 0.f;
     if (FLOWSRC == 1) {
-        dx = flow[(size_t)p * 2 * plane + o]; dy = flow[(size_t)p * 2 * plane + plane + o];
+        const float *f = flow + (size_t)p * 2 * plane + o;
+        dx = f[0]; dy = f[plane];
     } else if (FLOWSRC == 2) {
-        int cs = s >> 1;
+        constexpr int cs = S >> 1;
         const float *cf = coarse + (size_t)p * 2 * cs * cs;
-        dx = up2_sample(cf, cs, x, y); dy = up2_sample(cf + (size_t)cs * cs, cs, x, y);
+        dx = up2_sample(cf, cs, x, y); dy = up2_sample(cf + cs * cs, cs, x, y);
     }
     float m[5];
-    um_pixel(R0, R1, s, x, y, dx, dy, m);
-    float *M = Mall + (size_t)p * 5 * T * T;
-    M[o] = m[0]; M[plane + o] = m[1]; M[2 * plane + o] = m[2]; M[3 * plane + o] = m[3]; M[4 * plane + o] = m[4];
-    (void)flow_store;
+    um_pixel_c<S>(R0, R1, x, y, dx, dy, m);
+    float *M = Mall + (size_t)blockIdx.z * 5 * T * T + o;      // M is indexed by the pair's position in the (sub-)batch
+    M[0] = m[0]; M[plane] = m[1]; M[2 * plane] = m[2]; M[3 * plane] = m[3]; M[4 * plane] = m[4];
 }
 
-// ---- 15x15 box sums (float64) + 2x2 solve -------------------------------------------------------------
-// Warp-autonomous marching kernel: no shared memory, no block barriers.
-// A warp owns a strip of 128 columns (4 per lane; lanes 2..29 produce the 112 output columns, lanes 0,1,30,31
-// are the 8-column halo >= 7) and a segment of BX_SEG rows.  It marches down the segment keeping, per lane,
-// the vertical 15-row running sums of its 4 columns x 5 channels in float64 registers (run += new row - old
-// row: 2 adds per pixel-channel instead of 15).  The horizontal 15-column window is assembled from warp
-// shuffles of per-lane partial sums: window(j) = [T(t-1)+T(t)+T(t+1)] + suffix_{t-2}(j+1) + prefix_{t+2}(j).
-// float64 sums of <=225 float32 values are exact to ~1e-16, so any summation order agrees with the library's.
-// STATS: the last iteration of the finest level also emits per-task sums of |flow| and |flow|^2.
-// The segment length trades redundant window start-up (15 rows per segment) for parallelism: the small pyramid levels
-// are latency-bound (a few hundred warps for the whole GPU), so they use short segments.
-constexpr int BX_COLS = 112, BX_WARPS = 4, BS_M = 7;
-constexpr int BX_MIN_SEG = 8;
-__host__ __device__ constexpr int bx_strips(int s) { return (s + BX_COLS - 1) / BX_COLS; }
-__host__ __device__ constexpr int bx_segs(int s, int seg) { return (s + seg - 1) / seg; }
-
-__device__ __forceinline__ float4 ld_row4(const float *__restrict__ rowp, int xa, int xb, int s)
+// 15x15 box sums + 2x2 solve, one CHANNEL per warp.
+// A CTA of five warps owns a strip of 128 columns (112 outputs + 8 halo columns on each side) and a segment of rows of one
+// pair; warp c marches down the segment keeping the vertical 15-row running sums of channel c only in float64 registers
+// (4 columns per lane; run += entering row - leaving row: 2 adds per value instead of 15), assembles the horizontal
+// 15-column window from warp shuffles of per-lane partial sums -- window(j) = [T(t-1)+T(t)+T(t+1)] + suffix_{t-2}(j+1) +
+// prefix_{t+2}(j) -- and parks the four window sums of each lane in shared memory.  After one block barrier per TWO rows
+// (double-buffered) 112 threads solve one pixel each from the five sums and write the flow rows with coalesced stores.
+// float64 sums of <= 225 float32 values are exact to ~1e-16, so any summation order agrees with the library's.
+// Against round 1's one-warp-does-all-five-channels kernel: 5x the warps for the same pixels with no extra halo (the
+// small pyramid levels and small batches fill the GPU), 64 instead of 126 registers, a fifth of the serial float64 chain
+// per row; dense flow fields bit-identical (scripts/k2_fieldsha.py).
+// STATS: the last iteration of the finest level emits per-task sums of |flow| and |flow|^2 instead of the field.
+constexpr int BCS_THREADS = 160;
+template <int K, bool STATS>
+__global__ void __launch_bounds__(BCS_THREADS) box_cs_kernel(const float *__restrict__ Mall, float *__restrict__ flow, int seg_rows, int n_pairs,
+                                                            double *__restrict__ task_stats, int p_base)
 {
-    // 4 consecutive columns starting at xb (a multiple of 4); columns outside [0,s) replicate the edge column
-    float4 q;                                           // xa = clamp(xb, 0, s-4): always in range and 16-byte aligned
-#ifndef K2_VEC_ASM
-#define K2_VEC_ASM 0   /* measured: hand-placed ld.global.v4 doubles box_solve time (the compiler's own loads are software-pipelined) */
-#endif
-#if K2_VEC_ASM
-    asm("ld.global.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(q.x), "=f"(q.y), "=f"(q.z), "=f"(q.w) : "l"(rowp + xa));
-#else
-    q = *(const float4 *)(rowp + xa);
-#endif
-    if (xb < 0) q = make_float4(q.x, q.x, q.x, q.x);
-    else if (xb >= s) q = make_float4(q.w, q.w, q.w, q.w);
-    return q;
-}
-
-template <bool STATS>
-__global__ void __launch_bounds__(32 * BX_WARPS) box_solve_kernel(const float *__restrict__ Mall, float *__restrict__ flow, int k, int BX_SEG,
-                                                                 int n_pairs, double *__restrict__ task_stats, int p_base)
-{
-    const int s = lvl_size(k);
-    const int lane = threadIdx.x & 31;
-    const int tasks_per_pair = bx_strips(s) * bx_segs(s, BX_SEG);
-    const int task = blockIdx.x * BX_WARPS + (threadIdx.x >> 5);
-    if (task >= tasks_per_pair * n_pairs) return;
+    constexpr int S = lvl_size(K), STRIPS = bx_strips(S), plane = S * S;
+    __shared__ __align__(16) double asum[2][2][5][128];            // [phase][row of the pair][channel][column]
+    __shared__ double red[2][4];
+    const int lane = threadIdx.x & 31, c = threadIdx.x >> 5;
+    const int tasks_per_pair = STRIPS * bx_segs(S, seg_rows);
+    const int task = blockIdx.x;
     const int pl = task / tasks_per_pair, tp = task - pl * tasks_per_pair, p = pl + p_base;
-    const int strip = tp % bx_strips(s), seg = tp / bx_strips(s);
-    const int xb = strip * BX_COLS - 8 + 4 * lane, xa = clampi(xb, 0, s - 4);
-    const int y0 = seg * BX_SEG, y1 = min(y0 + BX_SEG, s);
-    const size_t plane = (size_t)s * s;
-    const float *M = Mall + (size_t)p * 5 * T * T;
-    const bool out_lane = lane >= 2 && lane < 30 && xb >= 0 && xb < s;
+    const int strip = tp % STRIPS, seg = tp / STRIPS;
+    const int xb = strip * BX_COLS - 8 + 4 * lane, xa = clampi(xb, 0, S - 4);
+    const int y0 = seg * seg_rows, y1 = min(y0 + seg_rows, S), nout = y1 - y0;
+    const float *M = Mall + (size_t)pl * 5 * T * T + c * plane + xa;
+    // columns outside the image replicate the edge column: a lane left of the image loads columns 0..3 and uses column 0
+    // for all four, a lane right of it loads S-4..S-1 and uses S-1 (the running sums of the other columns are never used)
+    const bool lo_edge = xb < 0, hi_edge = xb >= S;
+    auto row = [&](int r) { return *(const float4 *)(M + clampi(r, 0, S - 1) * S); };
 
-    double run[5][4];
-#pragma unroll
-    for (int c = 0; c < 5; c++) { run[c][0] = run[c][1] = run[c][2] = run[c][3] = 0.0; }
+    double r0 = 0.0, r1 = 0.0, r2 = 0.0, r3 = 0.0;
+#pragma unroll 5
     for (int j = -BS_M; j <= BS_M; j++) {
-        const float *rowp = M + (size_t)clampi(y0 + j, 0, s - 1) * s;
-#pragma unroll
-        for (int c = 0; c < 5; c++) {
-            float4 q = ld_row4(rowp + c * plane, xa, xb, s);
-            run[c][0] += (double)q.x; run[c][1] += (double)q.y; run[c][2] += (double)q.z; run[c][3] += (double)q.w;
-        }
+        const float4 q = row(y0 + j);
+        r0 += (double)q.x; r1 += (double)q.y; r2 += (double)q.z; r3 += (double)q.w;
     }
     const double scale = 1.0 / 225.0;
-    double sm = 0, sq = 0;
-    for (int y = y0; y < y1; y++) {
-        double a[5][4];
-#pragma unroll
-        for (int c = 0; c < 5; c++) {
-            const double v0 = run[c][0], v1 = run[c][1], v2 = run[c][2], v3 = run[c][3];
-            const double tot = (v0 + v1) + (v2 + v3);
-            const double mid = __shfl_up_sync(0xffffffffu, tot, 1) + tot + __shfl_down_sync(0xffffffffu, tot, 1);
-            const double l1 = __shfl_up_sync(0xffffffffu, v1, 2), l2 = __shfl_up_sync(0xffffffffu, v2, 2), l3 = __shfl_up_sync(0xffffffffu, v3, 2);
-            const double r0 = __shfl_down_sync(0xffffffffu, v0, 2), r1 = __shfl_down_sync(0xffffffffu, v1, 2), r2 = __shfl_down_sync(0xffffffffu, v2, 2);
-            const double s3 = l3, s2 = l2 + l3, s1 = l1 + s2;       // suffix sums of lane t-2 from local index 3,2,1
-            const double p1 = r0, p2 = r0 + r1, p3 = p2 + r2;       // prefix sums of lane t+2 of 1,2,3 columns
-            a[c][0] = (mid + s1) * scale;
-            a[c][1] = (mid + s2 + p1) * scale;
-            a[c][2] = (mid + s3 + p2) * scale;
-            a[c][3] = (mid + p3) * scale;
-        }
-        if (out_lane) {
-            float fx[4], fy[4];
-#pragma unroll
-            for (int j = 0; j < 4; j++) {
-                const double g11 = a[0][j], g12 = a[1][j], g22 = a[2][j], h1 = a[3][j], h2 = a[4][j];
-                const double idet = 1.0 / (g11 * g22 - g12 * g12 + 1e-3);
-                fx[j] = (float)((g11 * h2 - g12 * h1) * idet);
-                fy[j] = (float)((g22 * h1 - g12 * h2) * idet);
-                if (STATS) {
-                    const double mag = (double)sqrtf(fx[j] * fx[j] + fy[j] * fy[j]);   // float32 magnitude like np.sqrt(fx**2+fy**2)
-                    sm += mag; sq += mag * mag;
-                }
-            }
-            if (!STATS) {        // the statistics launch is the last of the chain: nobody reads its flow field
-                float *fo = flow + (size_t)p * 2 * plane + (size_t)y * s + xb;
-                *(float4 *)fo = make_float4(fx[0], fx[1], fx[2], fx[3]);
-                *(float4 *)(fo + plane) = make_float4(fy[0], fy[1], fy[2], fy[3]);
-            }
-        }
-        // slide the vertical window: + row y+8, - row y-7 (replicated borders)
-        const float *rn = M + (size_t)min(y + BS_M + 1, s - 1) * s, *ro = M + (size_t)max(y - BS_M, 0) * s;
-#pragma unroll
-        for (int c = 0; c < 5; c++) {
-            const float4 qn = ld_row4(rn + c * plane, xa, xb, s), qo = ld_row4(ro + c * plane, xa, xb, s);
-            run[c][0] += (double)qn.x - (double)qo.x; run[c][1] += (double)qn.y - (double)qo.y;
-            run[c][2] += (double)qn.z - (double)qo.z; run[c][3] += (double)qn.w - (double)qo.w;
-        }
-    }
-    if (STATS) {
-        // deterministic: fixed-order warp reduction, one partial per task, summed in task order afterwards
-        for (int o = 16; o; o >>= 1) { sm += __shfl_down_sync(0xffffffffu, sm, o); sq += __shfl_down_sync(0xffffffffu, sq, o); }
-        if (lane == 0) { size_t t = (size_t)p * tasks_per_pair + tp; task_stats[2 * t] = sm; task_stats[2 * t + 1] = sq; }
-    }
-}
-
-// ---- box_solve with an asynchronous row ring ---------------------------------------------------------------
-// Same arithmetic as box_solve_kernel, different data movement: every lane copies the rows it is going to need into its
-// own shared-memory ring with cp.async (LDGSTS), BXR-1 steps ahead, instead of holding them in registers; a lane only
-// ever reads what it copied itself, so the only synchronisation is cp.async.wait_group.  Measured (119 pairs, all 12
-// launches): direct loads 878 us, ring depth 2: 851 us, 3: 917 us, 4: 948 us, 6: 1379 us -- the kernel lives on resident
-// warps, not on prefetch distance, so the shallowest ring (40 KB per CTA, 4 CTAs per SM) is the default.
-// Step i < 15 brings window row y0-7+i; step 15+j brings the row that enters (y0+8+j) and the row that leaves (y0-7+j).
-#ifndef K2_BXR
-#define K2_BXR 2
-#endif
-constexpr int BXR = K2_BXR;                                   // ring depth (steps)
-constexpr int BXR_FLOAT4_PER_WARP = 2 * BXR * 5 * 32;    // 2 streams x ring x 5 channels x 32 lanes
-__device__ __forceinline__ void cp_async16(float4 *dst, const float *src)
-{
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
-}
-__device__ __forceinline__ float4 edge_fix(float4 q, int xb, int s)
-{
-    if (xb < 0) q = make_float4(q.x, q.x, q.x, q.x);
-    else if (xb >= s) q = make_float4(q.w, q.w, q.w, q.w);
-    return q;
-}
-
-template <bool STATS>
-__global__ void __launch_bounds__(32 * BX_WARPS, STATS ? 4 : 0) box_solve_ring_kernel(const float *__restrict__ Mall, float *__restrict__ flow, int k, int BX_SEG,
-                                                                      int n_pairs, double *__restrict__ task_stats, int p_base)
-{
-    extern __shared__ float4 bx_ring[];
-    const int s = lvl_size(k);
-    const int lane = threadIdx.x & 31;
-    const int tasks_per_pair = bx_strips(s) * bx_segs(s, BX_SEG);
-    const int task = blockIdx.x * BX_WARPS + (threadIdx.x >> 5);
-    if (task >= tasks_per_pair * n_pairs) return;
-    const int pl = task / tasks_per_pair, tp = task - pl * tasks_per_pair, p = pl + p_base;
-    const int strip = tp % bx_strips(s), seg = tp / bx_strips(s);
-    const int xb = strip * BX_COLS - 8 + 4 * lane, xa = clampi(xb, 0, s - 4);
-    const int y0 = seg * BX_SEG, y1 = min(y0 + BX_SEG, s), nout = y1 - y0;
-    const size_t plane = (size_t)s * s;
-    const float *M = Mall + (size_t)p * 5 * T * T + xa;
-    const bool out_lane = lane >= 2 && lane < 30 && xb >= 0 && xb < s;
-    float4 *ring = bx_ring + (threadIdx.x >> 5) * BXR_FLOAT4_PER_WARP + lane;
-    const int nsteps = 15 + nout - 1;
-
-    auto issue = [&](int i) {
-        if (i < nsteps) {
-            float4 *slot = ring + (i % BXR) * 5 * 32;
-            const float *ra = M + (size_t)clampi(y0 - BS_M + i, 0, s - 1) * s;
-#pragma unroll
-            for (int c = 0; c < 5; c++) cp_async16(slot + c * 32, ra + c * plane);
-            if (i >= 15) {
-                const float *rs = M + (size_t)max(y0 - BS_M + i - 15, 0) * s;
-#pragma unroll
-                for (int c = 0; c < 5; c++) cp_async16(slot + (BXR * 5 + c) * 32, rs + c * plane);
-            }
-        }
-        asm volatile("cp.async.commit_group;" ::: "memory");
+    // window sums of the current row for this warp's channel -> shared memory
+    auto emit = [&](double *dst4) {
+        double v0 = r0, v1 = r1, v2 = r2, v3 = r3;
+        if (lo_edge) { v1 = v0; v2 = v0; v3 = v0; }
+        if (hi_edge) { v0 = v3; v1 = v3; v2 = v3; }
+        const double tot = (v0 + v1) + (v2 + v3);
+        const double mid = __shfl_up_sync(0xffffffffu, tot, 1) + tot + __shfl_down_sync(0xffffffffu, tot, 1);
+        const double l1 = __shfl_up_sync(0xffffffffu, v1, 2), l2 = __shfl_up_sync(0xffffffffu, v2, 2), l3 = __shfl_up_sync(0xffffffffu, v3, 2);
+        const double n0 = __shfl_down_sync(0xffffffffu, v0, 2), n1 = __shfl_down_sync(0xffffffffu, v1, 2), n2 = __shfl_down_sync(0xffffffffu, v2, 2);
+        const double s3 = l3, s2 = l2 + l3, s1 = l1 + s2;       // suffix sums of lane t-2 from local index 3,2,1
+        const double p1 = n0, p2 = n0 + n1, p3 = p2 + n2;       // prefix sums of lane t+2 of 1,2,3 columns
+        ((double2 *)dst4)[0] = make_double2((mid + s1) * scale, (mid + s2 + p1) * scale);
+        ((double2 *)dst4)[1] = make_double2((mid + s3 + p2) * scale, (mid + p3) * scale);
     };
-#pragma unroll
-    for (int i = 0; i < BXR - 1; i++) issue(i);
-
-    double run[5][4];
-#pragma unroll
-    for (int c = 0; c < 5; c++) { run[c][0] = run[c][1] = run[c][2] = run[c][3] = 0.0; }
-    for (int i = 0; i < 15; i++) {
-        issue(i + BXR - 1);
-        asm volatile("cp.async.wait_group %0;" ::"n"(BXR - 1) : "memory");
-        const float4 *slot = ring + (i % BXR) * 5 * 32;
-#pragma unroll
-        for (int c = 0; c < 5; c++) {
-            const float4 q = edge_fix(slot[c * 32], xb, s);
-            run[c][0] += (double)q.x; run[c][1] += (double)q.y; run[c][2] += (double)q.z; run[c][3] += (double)q.w;
-        }
-    }
-    const double scale = 1.0 / 225.0;
+    // the window slides one row down: + entering row, - leaving row
+    auto slide = [&](const float4 &a, const float4 &b) {
+        r0 += (double)a.x - (double)b.x; r1 += (double)a.y - (double)b.y;
+        r2 += (double)a.z - (double)b.z; r3 += (double)a.w - (double)b.w;
+    };
+    const int t = threadIdx.x, px = strip * BX_COLS + t;
+    const bool solver = t < BX_COLS && px < S;
+    float *fo = flow + (size_t)p * 2 * plane + px;
     double sm = 0, sq = 0;
-    for (int j = 0; j < nout; j++) {
+    auto solve = [&](const double (*a)[128], int y) {
+        const double g11 = a[0][8 + t], g12 = a[1][8 + t], g22 = a[2][8 + t], h1 = a[3][8 + t], h2 = a[4][8 + t];
+        const double idet = 1.0 / (g11 * g22 - g12 * g12 + 1e-3);
+        const float fx = (float)((g11 * h2 - g12 * h1) * idet);
+        const float fy = (float)((g22 * h1 - g12 * h2) * idet);
+        if (STATS) {
+            const double mag = (double)sqrtf(fx * fx + fy * fy);     // float32 magnitude like np.sqrt(fx**2+fy**2)
+            sm += mag; sq += mag * mag;
+        } else {                                                      // the statistics launch is the last of the chain: nobody reads its flow field
+            fo[y * S] = fx;
+            fo[plane + y * S] = fy;
+        }
+    };
+    // two rows per block barrier; the rows that enter / leave the window (y -> y+1: rows y+8 and y-7) are fetched one
+    // iteration ahead, so their latency hides behind the barrier and the solve
+    float4 an = row(y0 + BS_M + 1), ao = row(y0 - BS_M), bn = row(y0 + BS_M + 2), bo = row(y0 - BS_M + 1);
+    int ph = 0;
+    for (int j = 0; j < nout; j += 2) {
         const int y = y0 + j;
-        double a[5][4];
-#pragma unroll
-        for (int c = 0; c < 5; c++) {
-            const double v0 = run[c][0], v1 = run[c][1], v2 = run[c][2], v3 = run[c][3];
-            const double tot = (v0 + v1) + (v2 + v3);
-            const double mid = __shfl_up_sync(0xffffffffu, tot, 1) + tot + __shfl_down_sync(0xffffffffu, tot, 1);
-            const double l1 = __shfl_up_sync(0xffffffffu, v1, 2), l2 = __shfl_up_sync(0xffffffffu, v2, 2), l3 = __shfl_up_sync(0xffffffffu, v3, 2);
-            const double r0 = __shfl_down_sync(0xffffffffu, v0, 2), r1 = __shfl_down_sync(0xffffffffu, v1, 2), r2 = __shfl_down_sync(0xffffffffu, v2, 2);
-            const double s3 = l3, s2 = l2 + l3, s1 = l1 + s2;       // suffix sums of lane t-2 from local index 3,2,1
-            const double p1 = r0, p2 = r0 + r1, p3 = p2 + r2;       // prefix sums of lane t+2 of 1,2,3 columns
-            a[c][0] = (mid + s1) * scale;
-            a[c][1] = (mid + s2 + p1) * scale;
-            a[c][2] = (mid + s3 + p2) * scale;
-            a[c][3] = (mid + p3) * scale;
+        emit(&asum[ph][0][c][4 * lane]);
+        slide(an, ao);
+        emit(&asum[ph][1][c][4 * lane]);                 // row y+1 (unused when it lies past the segment)
+        slide(bn, bo);
+        an = row(y + BS_M + 3); ao = row(y - BS_M + 2); bn = row(y + BS_M + 4); bo = row(y - BS_M + 3);
+        __syncthreads();
+        if (solver) {
+            solve(asum[ph][0], y);
+            if (y + 1 < y1) solve(asum[ph][1], y + 1);
         }
-        if (out_lane) {
-            float fx[4], fy[4];
-#pragma unroll
-            for (int jj = 0; jj < 4; jj++) {
-                const double g11 = a[0][jj], g12 = a[1][jj], g22 = a[2][jj], h1 = a[3][jj], h2 = a[4][jj];
-                const double idet = 1.0 / (g11 * g22 - g12 * g12 + 1e-3);
-                fx[jj] = (float)((g11 * h2 - g12 * h1) * idet);
-                fy[jj] = (float)((g22 * h1 - g12 * h2) * idet);
-                if (STATS) {
-                    const double mag = (double)sqrtf(fx[jj] * fx[jj] + fy[jj] * fy[jj]);   // float32 magnitude like np.sqrt(fx**2+fy**2)
-                    sm += mag; sq += mag * mag;
-                }
-            }
-            if (!STATS) {        // the statistics launch is the last of the chain: nobody reads its flow field
-                float *fo = flow + (size_t)p * 2 * plane + (size_t)y * s + xb;
-                *(float4 *)fo = make_float4(fx[0], fx[1], fx[2], fx[3]);
-                *(float4 *)(fo + plane) = make_float4(fy[0], fy[1], fy[2], fy[3]);
-            }
-        }
-        if (j + 1 < nout) {
-            // slide the vertical window: + row y+8, - row y-7 (replicated borders)
-            const int i = 15 + j;
-            issue(i + BXR - 1);
-            asm volatile("cp.async.wait_group %0;" ::"n"(BXR - 1) : "memory");
-            const float4 *slot = ring + (i % BXR) * 5 * 32;
-#pragma unroll
-            for (int c = 0; c < 5; c++) {
-                const float4 qn = edge_fix(slot[c * 32], xb, s), qo = edge_fix(slot[(BXR * 5 + c) * 32], xb, s);
-                run[c][0] += (double)qn.x - (double)qo.x; run[c][1] += (double)qn.y - (double)qo.y;
-                run[c][2] += (double)qn.z - (double)qo.z; run[c][3] += (double)qn.w - (double)qo.w;
-            }
-        }
+        ph ^= 1;
     }
     if (STATS) {
+        // deterministic: fixed-order warp reduction, then the four solver warps in order; one partial per task
         for (int o = 16; o; o >>= 1) { sm += __shfl_down_sync(0xffffffffu, sm, o); sq += __shfl_down_sync(0xffffffffu, sq, o); }
-        if (lane == 0) { size_t t = (size_t)p * tasks_per_pair + tp; task_stats[2 * t] = sm; task_stats[2 * t + 1] = sq; }
+        if (lane == 0 && c < 4) { red[0][c] = sm; red[1][c] = sq; }
+        __syncthreads();
+        if (t == 0) {
+            const size_t ti = (size_t)p * tasks_per_pair + tp;
+            task_stats[2 * ti] = ((red[0][0] + red[0][1]) + red[0][2]) + red[0][3];
+            task_stats[2 * ti + 1] = ((red[1][0] + red[1][1]) + red[1][2]) + red[1][3];
+        }
     }
 }
 
@@ -624,59 +500,47 @@ int k2_flow(avd_ctx *ctx, const uint8_t *d_prev, const uint8_t *d_next, size_t p
             AVD_LAUNCH(ctx, "polyexp", st, polyexp_kernel<<<dim3(s / PE_ROWS, ni), (s + 31) / 32 * 32, 3 * PE_ROWS * (s + 2 * PE_HALO) * sizeof(float), st>>>(pyr, R, k));
         }
         float *cur = flowA, *prev = flowB;
-        // Optional L2-resident sub-batching of levels 0/1 (AVD_K2_SB0 / AVD_K2_SB1 = pairs per sub-batch, 0 = off).
-        // Measured on B200 (profiles/r01_k2_notes.md): OFF is faster -- box_solve has only 30 warps of work per pair,
-        // so a 16-pair sub-batch leaves most SMs idle (box_solve 1.06 -> 4.1 ms, update_matrices 0.69 -> 0.84 ms).
-        // rows per box_solve segment, per level (AVD_K2_SEG="s0,s1,s2,s3" overrides; multiples of 8)
-        // 56 / 24 rows at levels 0 / 1: with 119 pairs (BASELINE's 120-sample clip) the launch is 536 / 417 CTAs, one wave of the
-        // 592 resident CTAs; 64 rows left a quarter of the slots empty at level 0 and 16 rows made level 1 595 CTAs, i.e. two waves.
-        // Fixed per level (not chosen per batch) so that a pair's flow never depends on the batch it is computed in.
-        static int seg_rows[4] = {56, 24, 8, 8};
+        // Flow iterations: um_kernel<K,.> + box_cs_kernel<K,.> per level, 3 iterations each.
+        // Rows per box segment, per level (AVD_K2_SEG="s0,s1,s2,s3"); fixed per level -- never chosen per batch -- so that a
+        // pair's flow does not depend on the batch it is computed in.  AVD_K2_SB="b0,b1,b2,b3": pairs per sub-batch at each
+        // level (0 = the whole batch; a sub-batch reuses the same M storage -- measured slower on B200 at every size tried,
+        // profiles/r02_k2_notes.md, kept as a tuning knob).
+        static int seg_rows[4] = {32, 24, 16, 8};
+        static int sub_batch[4] = {0, 0, 0, 0};
         static bool seg_init = false;
         if (!seg_init) {
             if (const char *e = getenv("AVD_K2_SEG")) sscanf(e, "%d,%d,%d,%d", &seg_rows[0], &seg_rows[1], &seg_rows[2], &seg_rows[3]);
+            if (const char *e = getenv("AVD_K2_SB")) sscanf(e, "%d,%d,%d,%d", &sub_batch[0], &sub_batch[1], &sub_batch[2], &sub_batch[3]);
             for (int &v : seg_rows) v = v < BX_MIN_SEG ? BX_MIN_SEG : v;
             seg_init = true;
         }
-        static const bool box_ring = !(getenv("AVD_K2_BOXRING") && atoi(getenv("AVD_K2_BOXRING")) == 0);
-        static bool ring_attr[64] = {};
-        if (box_ring && !ring_attr[ctx->device & 63]) {
-            const int bytes = (int)(BX_WARPS * BXR_FLOAT4_PER_WARP * sizeof(float4));
-            AVD_CUDA(ctx, cudaFuncSetAttribute(box_solve_ring_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
-            AVD_CUDA(ctx, cudaFuncSetAttribute(box_solve_ring_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
-            ring_attr[ctx->device & 63] = true;
-        }
-        static int sb0 = getenv("AVD_K2_SB0") ? atoi(getenv("AVD_K2_SB0")) : 0, sb1 = getenv("AVD_K2_SB1") ? atoi(getenv("AVD_K2_SB1")) : 0;
+        const bool want_stats = d_rec_first != nullptr;
+        // AVD_K2_LEVEL_NAMES=1: the per-kernel timing log (avd_profile_read) keeps the pyramid levels apart
+        static const bool lvl_names = getenv("AVD_K2_LEVEL_NAMES") && atoi(getenv("AVD_K2_LEVEL_NAMES"));
+        static const char *um_name[4] = {"update_matrices_L0", "update_matrices_L1", "update_matrices_L2", "update_matrices_L3"};
+        static const char *box_name[4] = {"box_solve_L0", "box_solve_L1", "box_solve_L2", "box_solve_L3"};
         for (int k = 3; k >= 0; k--) {
             const int s = lvl_size(k);
-            const int SB = k == 0 ? (sb0 > 0 ? sb0 : np) : k == 1 ? (sb1 > 0 ? sb1 : np) : np;
+            const int SB = sub_batch[k] > 0 && sub_batch[k] < np ? sub_batch[k] : np;
+            const int seg = seg_rows[k];
             for (int q0 = 0; q0 < np; q0 += SB) {
                 const int nq = np - q0 < SB ? np - q0 : SB;
                 dim3 gu((s + 31) / 32, (s + 7) / 8, nq), bu(32, 8);
-                const int seg = seg_rows[k];
-                const int bx_blocks = (bx_strips(s) * bx_segs(s, seg) * nq + BX_WARPS - 1) / BX_WARPS;
-                if (k == 3) {
-                    AVD_LAUNCH(ctx, "update_matrices", st, update_matrices_kernel<0><<<gu, bu, 0, st>>>(R, nullptr, nullptr, M, nullptr, k, mode, q0));
-                } else {
-                    AVD_LAUNCH(ctx, "update_matrices", st, update_matrices_kernel<2><<<gu, bu, 0, st>>>(R, nullptr, prev, M, nullptr, k, mode, q0));
-                }
-                for (int it = 0; it < 3; it++) {
-                    const size_t ring_bytes = (size_t)BX_WARPS * BXR_FLOAT4_PER_WARP * sizeof(float4);
-                    if (box_ring) {
-                        if (k == 0 && it == 2 && d_rec_first) {
-                            AVD_LAUNCH(ctx, "box_solve", st, box_solve_ring_kernel<true><<<bx_blocks, 32 * BX_WARPS, ring_bytes, st>>>(M, cur, k, seg, nq, tile_stats, q0));
-                        } else {
-                            AVD_LAUNCH(ctx, "box_solve", st, box_solve_ring_kernel<false><<<bx_blocks, 32 * BX_WARPS, ring_bytes, st>>>(M, cur, k, seg, nq, nullptr, q0));
-                        }
-                    } else if (k == 0 && it == 2 && d_rec_first) {
-                        AVD_LAUNCH(ctx, "box_solve", st, box_solve_kernel<true><<<bx_blocks, 32 * BX_WARPS, 0, st>>>(M, cur, k, seg, nq, tile_stats, q0));
-                    } else {
-                        AVD_LAUNCH(ctx, "box_solve", st, box_solve_kernel<false><<<bx_blocks, 32 * BX_WARPS, 0, st>>>(M, cur, k, seg, nq, nullptr, q0));
-                    }
-                    if (it < 2) {
-                        AVD_LAUNCH(ctx, "update_matrices", st, update_matrices_kernel<1><<<gu, bu, 0, st>>>(R, cur, nullptr, M, nullptr, k, mode, q0));
-                    }
-                }
+                const int tasks = bx_strips(s) * bx_segs(s, seg) * nq;
+#define UM_LAUNCH(K, SRC, FLOW, COARSE) AVD_LAUNCH(ctx, (lvl_names ? um_name[K] : "update_matrices"), st, um_kernel<K, SRC><<<gu, bu, 0, st>>>(R, FLOW, COARSE, M, mode, q0))
+#define BOX_LAUNCH(K, STATS) AVD_LAUNCH(ctx, (lvl_names ? box_name[K] : "box_solve"), st, box_cs_kernel<K, STATS><<<tasks, BCS_THREADS, 0, st>>>(M, cur, seg, nq, STATS ? tile_stats : nullptr, q0))
+#define LEVEL(K)                                                                                  \
+    {                                                                                             \
+        if (K == 3) UM_LAUNCH(K, 0, nullptr, nullptr); else UM_LAUNCH(K, 2, nullptr, prev);       \
+        for (int it = 0; it < 3; it++) {                                                          \
+            if (K == 0 && it == 2 && want_stats) BOX_LAUNCH(K, true); else BOX_LAUNCH(K, false);  \
+            if (it < 2) UM_LAUNCH(K, 1, cur, nullptr);                                            \
+        }                                                                                         \
+    }
+                if (k == 3) LEVEL(3) else if (k == 2) LEVEL(2) else if (k == 1) LEVEL(1) else LEVEL(0)
+#undef LEVEL
+#undef BOX_LAUNCH
+#undef UM_LAUNCH
             }
             float *t = cur; cur = prev; prev = t;   // prev now holds this level's flow
         }

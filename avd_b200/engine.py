@@ -186,10 +186,19 @@ class Engine:
         return out
 
     def analyze_device(self, frames, prev_frame=None):
-        """Whole device path for frames resident in HBM: K1 + K2.  Returns NumPy records (n,) REC_DTYPE.
-        prev_frame: optional (H,W,3) CUDA tensor, the sample before frames[0] (chunk halo)."""
+        """Whole device path for frames resident in HBM: K1 + K2.  Returns the (n, 160) uint8 CUDA tensor of records.
+        prev_frame: optional (H,W,3) CUDA tensor, the sample before frames[0] (chunk halo).  When the halo frame sits
+        directly in front of `frames` in memory (one staging buffer: [halo, f0, f1, ...]) the n + 1 frames go through ONE
+        K1 launch and one K2 pass and the halo's record is dropped; otherwise the halo gets its own one-frame K1 launch."""
         import torch
         if prev_frame is not None:
+            n, fb = frames.shape[0], frames.stride(0)
+            if (n > 0 and prev_frame.is_contiguous() and frames[0].is_contiguous() and prev_frame.shape == frames.shape[1:]
+                    and prev_frame.data_ptr() + fb == frames.data_ptr() and fb == prev_frame.numel()):
+                both = torch.as_strided(prev_frame, (n + 1,) + tuple(frames.shape[1:]), frames.stride())
+                rec, thumbs = self.frames_features(both)
+                self.flow_stats(thumbs, rec)
+                return rec[1:]
             rec0, th0 = self.frames_features(prev_frame[None])
             prev_hash = rec0.view(torch.int32)[0, 6:38]          # hash words: bytes 24..152
             rec, thumbs = self.frames_features(frames, prev_hash=prev_hash)
@@ -242,43 +251,66 @@ class Engine:
 
     # -- host path (the public, torch-free call) --------------------------------------------------------
     def analyze_host(self, frames, keep_on_device: bool = False, fmt: str = "bgr", shape=None):
-        """frames: sequence of (H,W,3) uint8 arrays (same shape, rows contiguous) or one (n,H,W,3) array,
-        ideally in pinned memory (`Engine.pinned`).  Streams them through K1/K2 and returns records.
+        """frames: sequence of (H,W,3) uint8 arrays (same shape, rows contiguous), one (n,H,W,3) array, or a prepared
+        `HostBatch`; ideally in pinned memory (`Engine.pinned`).  Streams them through K1/K2 and returns records.
         keep_on_device: leave the records in HBM for `scoring.score_jobs` (K3) and return None.
         fmt "i420" / "j420" (with shape=(H, W)): every frame is a dense planar 4:2:0 picture of 1.5*H*W bytes as the
         decoder emits it (limited / full range); the colour conversion of cv2's retrieve() then runs on the device."""
-        n = len(frames)
-        out = None if keep_on_device else np.zeros(n, REC_DTYPE)
-        if n == 0:
+        b = frames if isinstance(frames, HostBatch) else HostBatch(frames, fmt, shape)
+        out = None if keep_on_device else np.zeros(b.n, REC_DTYPE)
+        if b.n == 0:
             return out
-        if fmt != "bgr":
-            if fmt not in ("i420", "j420") or shape is None:
-                raise AvdError("analyze_host: fmt must be 'bgr', 'i420' or 'j420' (the latter two with shape=(H, W))")
-            H, W = int(shape[0]), int(shape[1])
-            ptrs = (C.c_void_p * n)()
-            for i in range(n):
-                f = frames[i]
-                if f.dtype != np.uint8 or f.size != H * W * 3 // 2 or not f.flags["C_CONTIGUOUS"]:
-                    raise AvdError("analyze_host: 4:2:0 frames must be contiguous uint8 arrays of 1.5*H*W bytes")
-                ptrs[i] = f.ctypes.data
-            with self._lock:
-                self._check(self.L.avd_analyze_host_yuv420(self.h, ptrs, n, H, W, int(fmt == "j420"),
-                                                           C.c_void_p(out.ctypes.data) if out is not None else None),
-                            "avd_analyze_host_yuv420")
-            return out
-        f0 = frames[0]
-        H, W = int(f0.shape[0]), int(f0.shape[1])
-        pitch = int(f0.strides[0])
-        ptrs = (C.c_void_p * n)()
-        for i in range(n):
-            f = frames[i]
-            if f.dtype != np.uint8 or f.shape != (H, W, 3) or f.strides[2] != 1 or f.strides[1] != 3 or f.strides[0] != pitch:
-                raise AvdError("analyze_host: frames must be uint8 (H,W,3), packed BGR, one common shape and row pitch")
-            ptrs[i] = f.ctypes.data
+        o = C.c_void_p(out.ctypes.data) if out is not None else None
         with self._lock:
-            self._check(self.L.avd_analyze_host(self.h, ptrs, n, H, W, pitch,
-                                                C.c_void_p(out.ctypes.data) if out is not None else None), "avd_analyze_host")
+            if b.fmt == "bgr":
+                self._check(self.L.avd_analyze_host(self.h, b.ptrs, b.n, b.H, b.W, b.pitch, o), "avd_analyze_host")
+            else:
+                self._check(self.L.avd_analyze_host_yuv420(self.h, b.ptrs, b.n, b.H, b.W, int(b.fmt == "j420"), o), "avd_analyze_host_yuv420")
         return out
+
+
+class HostBatch:
+    """Validated frame pointers of one `analyze_host` run.  Building it costs a few microseconds per frame (Python), so a
+    caller that re-uses its staging buffers (a server, the decode pipeline of video.analyze) prepares it once per buffer:
+    it stays valid while the frames keep their addresses and shapes (the contents may change)."""
+
+    def __init__(self, frames, fmt: str = "bgr", shape=None):
+        if fmt not in ("bgr", "i420", "j420"):
+            raise AvdError("frame format must be 'bgr', 'i420' or 'j420'")
+        self.fmt, self.n, self.keepalive = fmt, len(frames), frames
+        self.H = self.W = self.pitch = 0
+        self.ptrs = None
+        if self.n == 0:
+            return
+        if fmt == "bgr":
+            f0 = frames[0]
+            self.H, self.W, self.pitch = int(f0.shape[0]), int(f0.shape[1]), int(f0.strides[0])
+            per_frame = (self.H, self.W, 3)
+            ok = lambda f: (f.dtype == np.uint8 and f.shape == per_frame and f.strides[2] == 1 and f.strides[1] == 3
+                            and f.strides[0] == self.pitch)
+            err = "analyze_host: frames must be uint8 (H,W,3), packed BGR, one common shape and row pitch"
+        else:
+            if shape is None:
+                raise AvdError("analyze_host: 4:2:0 frames need shape=(H, W)")
+            self.H, self.W = int(shape[0]), int(shape[1])
+            self.pitch = 3 * self.W
+            nb = self.H * self.W * 3 // 2
+            ok = lambda f: f.dtype == np.uint8 and f.size == nb and f.flags["C_CONTIGUOUS"]
+            err = "analyze_host: 4:2:0 frames must be contiguous uint8 arrays of 1.5*H*W bytes"
+        if isinstance(frames, np.ndarray) and frames.ndim >= 2:
+            # one array of n frames: validate one frame, compute the addresses arithmetically
+            if not ok(frames[0]):
+                raise AvdError(err)
+            addr = frames.ctypes.data + np.arange(self.n, dtype=np.uint64) * np.uint64(frames.strides[0])
+        else:
+            addr = np.empty(self.n, np.uint64)
+            for i in range(self.n):
+                f = frames[i]
+                if not ok(f):
+                    raise AvdError(err)
+                addr[i] = f.__array_interface__["data"][0]
+        self._addr = addr
+        self.ptrs = addr.ctypes.data_as(C.POINTER(C.c_void_p))
 
 
 # ---- process-wide engines ------------------------------------------------------------------------------------

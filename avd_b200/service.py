@@ -2,7 +2,8 @@
 analyzers (`api.py:143-169`), with the two things the GPU path makes worth doing:
 
 * `analyze_path` runs the audio and the video analyzer of one request side by side (the reference awaits them one after
-  the other, `api.py:145-146`): their decodes (ffmpeg, cv2) overlap, the GPU calls are serialised by the engine's lock.
+  the other, `api.py:145-146`): their decodes (ffmpeg, cv2) overlap; each analyzer call leases its own context from the device's engine pool
+  (engine.lease), so concurrent requests overlap on the GPU as well.
   Failures are replaced by the reference's neutral results and recorded in the hints exactly as `_safe_audio` /
   `_safe_video` do (`api.py:118-141`).
 * `RequestBatcher` coalesces requests that arrive together on the server's pool threads (`api.py:133`) into one

@@ -122,8 +122,8 @@ class _RunPipeline:
     def _frames(self, stage, lo, hi):
         if self.fmt == "bgr":
             H, W = self.shape
-            return [stage[i].reshape(H, W, 3) for i in range(lo, hi)]
-        return [stage[i] for i in range(lo, hi)]
+            return stage[lo:hi].reshape(hi - lo, H, W, 3)
+        return stage[lo:hi]
 
     def _run(self, stage, lo, hi, drop_first):
         recs = self.eng.analyze_host(self._frames(stage, lo, hi), fmt=self.fmt, shape=self.shape)

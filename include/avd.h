@@ -205,15 +205,16 @@ int avd_profile_enable(avd_ctx *ctx, int on);
 int avd_profile_read(avd_ctx *ctx, char *buf, size_t cap);
 
 /* Select the per-frame kernel: 0 = auto (streaming fused kernel when W % 64 == 0, 640 <= W,H <= 4096 and buffers
- * are 16-byte aligned; banded fused kernel when W % 16 == 0; generic otherwise), 1 = force the generic
- * multi-kernel path, 2 = skip the streaming kernel (banded or generic).  For tests. */
+ * are 16-byte aligned; banded fused kernel when W % 16 == 0; any-width fused kernel when a band of gray rows fits in
+ * shared memory; generic multi-kernel path otherwise), 1 = force the generic path, 2 = skip the streaming kernel,
+ * 3 = skip the streaming and the banded kernel (any-width fused kernel, or generic).  For tests. */
 int avd_set_k1_mode(avd_ctx *ctx, int mode);
 
 /*
  * Host-only view of the per-shape plan the frame kernels run from (no device needed): band ownership of source
  * rows, INTER_LINEAR taps (video.py:43), thumbnail columns per 16-pixel strip, thumbnail role of every source row
  * (bit0 tap row, bit1 bottom tap, bits 2-13 vertical weight, bits 16-24 thumbnail row) and the kernel a dense
- * aligned buffer of this shape is given (0 streaming fused, 2 banded fused, 1 generic).  For tests and debugging.
+ * aligned buffer of this shape is given (0 streaming fused, 2 banded fused, 3 any-width fused, 1 generic).  For tests and debugging.
  */
 typedef struct avd_shape_plan_t {
     int area_int, thumb_2x2, strip_ntx_max, k1_path;

@@ -34,6 +34,12 @@ def run(fn):
 direct = lambda f, m: video.analyze_frames(f, m, engine=eng)
 run(direct)
 a = run(direct)
+pooled = lambda f, m: video.analyze_frames(f, m)              # engine=None: a context leased from the device's pool per request
+run(pooled)
+ap = run(pooled)
+from avd_b200.engine import engine_pool
+print(f"8 threads, 10 x 720p frames per request: one shared context {a:.0f} requests/s; pool of {engine_pool(0).size} contexts "
+      f"(AVD_ENGINES_PER_DEVICE) {ap:.0f} requests/s ({10*ap:.0f} frames/s)")
 for wait in (0.5, 1.0, 2.0):
     b = service.RequestBatcher(engine=eng, max_wait_ms=wait)
     run(b.analyze_frames)

@@ -61,6 +61,46 @@ def test_sharded_equals_single_gpu_nccl(tmp_path):
     assert "MULTI_OK" in out.stdout
 
 
+_WORKER_ONE_GPU = r"""
+import os, sys, json, numpy as np
+sys.path.insert(0, {root!r})
+import torch, torch.distributed as dist
+from avd_b200 import dist as avd_dist, video
+from avd_b200.engine import Engine
+import avd_b200.synth as synth
+rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+dist.init_process_group("gloo")
+eng = Engine(0)                                              # every rank computes on cuda:0; records travel over gloo
+clip = synth.Clip(450, 1080, 1920, seed=2, fps=30.0)
+frames = clip.sampled(15)                                    # 30 samples at BASELINE configs[1] geometry
+meta = {{"fps": 30.0, "width": 1920, "height": 1080, "duration": 15.0}}
+lo, hi, halo = avd_dist.local_range_with_halo(len(frames), rank, world)
+res, full = avd_dist.analyze_frames_sharded(frames[lo:hi], frames[halo] if halo is not None else None, len(frames), meta,
+                                            rank, world, eng.analyze_host, device=None)
+single = eng.analyze_host(frames)
+assert full.tobytes() == single.tobytes(), "sharded records differ from the single-GPU run"
+assert res == video.analyze_frames(frames, meta, engine=eng)
+dist.barrier()
+if rank == 0:
+    print("ONE_GPU_MULTI_OK")
+dist.destroy_process_group()
+"""
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_sharded_ranks_on_one_gpu_equal_single_run(tmp_path, world):
+    """The sharded path end to end on a ONE-GPU box (where the NCCL test above has to skip): `world` processes, each
+    analysing its chunk (+ one-sample halo) with the real kernels on cuda:0, records all-gathered over gloo; the
+    assembled records must equal the single run byte for byte on every rank.  The kernels of the ranks are independent
+    launches (nothing waits on another rank on the device)."""
+    script = tmp_path / "w1.py"
+    script.write_text(_WORKER_ONE_GPU.format(root=ROOT))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr", "127.0.0.1",
+           "--master-port", str(29551 + world), str(script)]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
+    assert out.returncode == 0 and "ONE_GPU_MULTI_OK" in out.stdout, out.stdout[-3000:] + out.stderr[-3000:]
+
+
 def test_clip_batch_equals_per_clip(synth):
     """Single GPU: one batched run over several clips == analysing each clip on its own."""
     from avd_b200 import video

@@ -52,12 +52,12 @@ def test_extension_is_loaded_and_native(eng):
     assert eng.launches == 0
 
 
-@pytest.mark.parametrize("mode", [0, 1, 2])
+@pytest.mark.parametrize("mode", [0, 1, 2, 3])
 @pytest.mark.parametrize("idx", range(13))
 def test_frame_features_vs_reference_golden(golden, golden_arrays, synth, torch, eng, idx, mode):
     """Every library code path (general / integer INTER_AREA, 2x2 INTER_LINEAR shortcut, upsampling, odd
     widths, 32x32 minimum, 4K) against what cv2 produced for the reference; all three K1 implementations
-    (0 = streaming fused kernel where the shape allows, 1 = generic, 2 = banded fused kernel)."""
+    (0 = streaming fused kernel where the shape allows, 1 = generic, 2 = banded fused kernel, 3 = any-width fused kernel)."""
     c = golden["frames"][idx]
     f = _frame(synth, c)
     eng.set_k1_mode(mode)
@@ -84,13 +84,50 @@ def test_fused_equals_generic_on_batches(synth, torch, eng):
         clip = synth.Clip(40, H, W, seed=5, events=True)
         fr = torch.from_numpy(np.stack([clip[i] for i in (0, 3, 12, 13, 20, 25, 31, 39)])).cuda()
         outs = []
-        for mode in (0, 1, 2):
+        for mode in (0, 1, 2, 3):
             eng.set_k1_mode(mode)
             rec, th, ar = eng.frames_features(fr, want_area32=True)
             outs.append((rec.cpu().numpy().tobytes(), th.cpu().numpy().tobytes(), ar.cpu().numpy().tobytes()))
         eng.set_k1_mode(0)
         assert outs[0] == outs[1], (H, W, "streaming vs generic")
         assert outs[2] == outs[1], (H, W, "banded vs generic")
+        assert outs[3] == outs[1], (H, W, "any-width fused vs generic")
+
+
+def test_any_width_kernel_equals_generic_on_ragged_shapes(synth, torch, eng, oracle):
+    """k1_rows.cu: widths that are not a multiple of 16 (854x480 of BASELINE configs[4], 1366x768, odd crops), the 2x2
+    thumbnail shortcut, thumbnail upsampling, the 32x32 minimum, unaligned views -- byte for byte the generic path, and the
+    oracle on one frame per shape."""
+    for (H, W) in [(480, 854), (768, 1366), (333, 777), (144, 256), (640, 640), (32, 32), (33, 35), (641, 1283), (1080, 1918), (100, 150)]:
+        clip = synth.Clip(12, H, W, seed=15, events=False, pan=3)
+        host = np.stack([clip[i] for i in (0, 1, 5, 5, 11)])
+        fr = torch.from_numpy(host).cuda()
+        outs = {}
+        for mode in (1, 3):
+            eng.set_k1_mode(mode)
+            rec, th, ar = eng.frames_features(fr, want_area32=True)
+            outs[mode] = (rec.cpu().numpy().tobytes(), th.cpu().numpy().tobytes(), ar.cpu().numpy().tobytes())
+        eng.set_k1_mode(0)
+        assert outs[3] == outs[1], (H, W)
+        rec, th = eng.frames_features(fr)                               # auto: what a caller gets
+        assert (rec.cpu().numpy().tobytes(), th.cpu().numpy().tobytes()) == outs[1][:2], (H, W)
+        g = oracle.gray(host[1])
+        r = _rec_np(eng, rec)[1]
+        assert (int(r["lap_sum"]), int(r["lap_sumsq"])) == oracle.lap_sums(g)
+        assert np.array_equal(r["hash"], oracle.hash_words(oracle.area32(g))) and np.array_equal(th[1].cpu().numpy(), oracle.thumb320(g))
+    # a view that is not even 4-byte aligned (byte path of the gray stage)
+    H, W = 120, 203
+    f = synth.noise_frames(2, H, W, 19)
+    big = torch.zeros((2, H, W * 3 + 7), dtype=torch.uint8, device="cuda")
+    big[:, :, 3:3 + W * 3] = torch.from_numpy(f.reshape(2, H, W * 3)).cuda()
+    view = big[:, :, 3:3 + W * 3].unflatten(2, (W, 3))
+    outs = {}
+    for mode in (1, 3):
+        eng.set_k1_mode(mode)
+        rec, th, ar = eng.frames_features(view, want_area32=True)
+        outs[mode] = (rec.cpu().numpy().tobytes(), th.cpu().numpy().tobytes(), ar.cpu().numpy().tobytes())
+    eng.set_k1_mode(0)
+    assert outs[3] == outs[1]
 
 
 def test_area_rounding_boundaries(torch, eng, oracle):

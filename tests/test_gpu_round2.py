@@ -243,3 +243,20 @@ def test_engine_pool_serves_concurrent_requests(synth):
     [t.join() for t in ts]
     assert not errs and got == want
     assert 1 <= len(engine_pool(0)._all) <= engine_pool(0).size
+
+
+def test_halo_frame_folded_into_the_main_launch(synth, torch, eng):
+    """A chunk whose halo sample sits directly in front of it in memory goes through one K1 launch and one K2 pass
+    (engine.analyze_device); the records must be those of the separate-halo path and of the unsharded run."""
+    clip = synth.Clip(60, 720, 1280, seed=77, events=True, pan=2)
+    allf = torch.from_numpy(np.stack([clip[i] for i in range(0, 60, 5)])).cuda()          # 12 samples
+    whole = eng.analyze_device(allf).cpu().numpy().tobytes()
+    l0 = eng.launches
+    folded = eng.analyze_device(allf[1:], prev_frame=allf[0]).cpu().numpy().tobytes()
+    n_folded = eng.launches - l0
+    halo = allf[0].clone()
+    l0 = eng.launches
+    separate = eng.analyze_device(allf[1:], prev_frame=halo).cpu().numpy().tobytes()
+    n_separate = eng.launches - l0
+    assert folded == separate == whole[160:]
+    assert n_folded < n_separate

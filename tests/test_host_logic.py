@@ -261,10 +261,11 @@ def test_shape_plan_row_roles(shape):
 
 
 def test_shape_plan_kernel_choice():
-    """Which per-frame kernel a dense aligned buffer gets: 0 streaming fused, 2 banded fused, 1 generic."""
+    """Which per-frame kernel a dense aligned buffer gets: 0 streaming fused, 2 banded fused, 3 any-width fused (a band of
+    gray rows in shared memory), 1 generic (bands too large for shared memory)."""
     want = {(1080, 1920): 0, (720, 1280): 0, (1440, 2560): 0, (2160, 3840): 0, (648, 1344): 0, (960, 1280): 0,
             (480, 640): 2, (640, 640): 2, (360, 640): 2, (1080, 1936): 2,   # W % 16 == 0 only
-            (480, 854): 1, (333, 777): 1, (32, 32): 2,
+            (480, 854): 3, (333, 777): 3, (768, 1366): 3, (32, 32): 2, (2160, 3838): 1, (33, 35): 3,
             (600, 1920): 2}                                                   # H < 640: a tap row would have two roles
     for (H, W), k in want.items():
         assert _plan(H, W).k1_path == k, (H, W)
