@@ -50,37 +50,64 @@ __global__ void __launch_bounds__(KR_THREADS) k1_rows_kernel(KRParams P)
     __shared__ long long red[2][KR_THREADS / 32];
     const uint8_t *frame = P.bgr + (size_t)f * P.fstride;
 
-    // ---- gray rows of the band ------------------------------------------------------------------------------------------
+    // ---- gray rows of the band: a warp per row, a lane per group of 4 pixels (12 bytes) -------------------------------------
+    const int lane = tid & 31, wid = tid >> 5;
     const int groups = (W + 3) >> 2;
-    for (int i = tid; i < nseq * groups; i += KR_THREADS) {
-        const int q = i / groups, g4 = i - q * groups, x = 4 * g4;
+    for (int q = wid; q < nseq; q += KR_THREADS / 32) {
         const int r = r101(own0 - 1 + q, H);
-        const uint8_t *src = frame + (size_t)r * P.pitch + 3 * (size_t)x;
-        uint32_t out;
-        if (P.aligned4 && x + 4 <= W) {
-            const uint32_t w0 = ((const uint32_t *)src)[0], w1 = ((const uint32_t *)src)[1], w2 = ((const uint32_t *)src)[2];
-            out = gray_of(w0 & 255u, (w0 >> 8) & 255u, (w0 >> 16) & 255u)
-                | gray_of(w0 >> 24, w1 & 255u, (w1 >> 8) & 255u) << 8
-                | gray_of((w1 >> 16) & 255u, w1 >> 24, w2 & 255u) << 16
-                | gray_of((w2 >> 8) & 255u, (w2 >> 16) & 255u, w2 >> 24) << 24;
-        } else {
-            out = 0;
-            for (int k = 0; k < 4 && x + k < W; k++) out |= gray_of(src[3 * k], src[3 * k + 1], src[3 * k + 2]) << (8 * k);
+        const uint8_t *rowp = frame + (size_t)r * P.pitch;
+        uint32_t *grow = (uint32_t *)(G + (size_t)q * Wp);
+        for (int g4 = lane; g4 < groups; g4 += 32) {
+            const int x = 4 * g4;
+            const uint8_t *src = rowp + 3 * x;
+            uint32_t out;
+            if (P.aligned4 && x + 4 <= W) {
+                const uint32_t w0 = ((const uint32_t *)src)[0], w1 = ((const uint32_t *)src)[1], w2 = ((const uint32_t *)src)[2];
+                out = gray_of(w0 & 255u, (w0 >> 8) & 255u, (w0 >> 16) & 255u)
+                    | gray_of(w0 >> 24, w1 & 255u, (w1 >> 8) & 255u) << 8
+                    | gray_of((w1 >> 16) & 255u, w1 >> 24, w2 & 255u) << 16
+                    | gray_of((w2 >> 8) & 255u, (w2 >> 16) & 255u, w2 >> 24) << 24;
+            } else {
+                out = 0;
+                for (int k = 0; k < 4 && x + k < W; k++) out |= gray_of(src[3 * k], src[3 * k + 1], src[3 * k + 2]) << (8 * k);
+            }
+            grow[g4] = out;
         }
-        *(uint32_t *)(G + (size_t)q * Wp + x) = out;
     }
     __syncthreads();
 
-    // ---- Laplacian sums over the owned rows (sequence rows 1 .. n) ----------------------------------------------------------
-    long long s = 0, ss = 0;
-    for (int i = tid; i < n * W; i += KR_THREADS) {
-        const int q = 1 + i / W, x = i - (q - 1) * W;
+    // ---- Laplacian sums over the owned rows (sequence rows 1 .. n): a warp per row, 4 pixels per lane and step -----------------
+    long long s = 0;
+    unsigned long long ss = 0;
+    for (int q = 1 + wid; q <= n; q += KR_THREADS / 32) {
         const uint8_t *c = G + (size_t)q * Wp;
-        const int L = (int)c[x - Wp] + (int)c[x + Wp] + (int)c[r101(x - 1, W)] + (int)c[r101(x + 1, W)] - 4 * (int)c[x];
-        s += L; ss += L * L;
+        int rs = 0;
+        unsigned rss = 0;                                       // <= 128 pixels per lane and row at W <= 4096: < 2^31
+        for (int x = 4 * lane; x < W; x += 128) {
+            const uint32_t cw = *(const uint32_t *)(c + x), uw = *(const uint32_t *)(c + x - Wp), dw = *(const uint32_t *)(c + x + Wp);
+            const int left = c[x == 0 ? 1 : x - 1];
+            const int cnt = min(4, W - x);
+            int pv[6];
+            pv[0] = left;
+#pragma unroll
+            for (int k = 0; k < 4; k++) pv[1 + k] = (int)((cw >> (8 * k)) & 255u);
+            pv[5] = x + 4 < W ? (int)c[x + 4] : 0;
+            const bool lastg = x + cnt == W;
+#pragma unroll
+            for (int k = 0; k < 4; k++)
+                if (k < cnt) {
+                    const int right = (lastg && k + 1 == cnt) ? pv[k] : pv[k + 2];     // REFLECT_101: right of W-1 is W-2
+                    const int L = (int)((uw >> (8 * k)) & 255u) + (int)((dw >> (8 * k)) & 255u) + pv[k] + right - 4 * pv[k + 1];
+                    rs += L; rss += (unsigned)(L * L);
+                }
+        }
+        s += rs; ss += rss;
     }
-    for (int o = 16; o; o >>= 1) { s += __shfl_down_sync(0xffffffffu, s, o); ss += __shfl_down_sync(0xffffffffu, ss, o); }
-    if ((tid & 31) == 0) { red[0][tid >> 5] = s; red[1][tid >> 5] = ss; }
+    {
+        long long ss2 = (long long)ss;
+        for (int o = 16; o; o >>= 1) { s += __shfl_down_sync(0xffffffffu, s, o); ss2 += __shfl_down_sync(0xffffffffu, ss2, o); }
+        if (lane == 0) { red[0][wid] = s; red[1][wid] = ss2; }
+    }
 
     // ---- thumbnail rows whose top tap row this band owns ---------------------------------------------------------------------
     {

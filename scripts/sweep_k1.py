@@ -37,7 +37,7 @@ def _cpu_worker(args):
 def main():
     import multiprocessing as mp
     cores = len(os.sched_getaffinity(0))
-    shapes = [(480, 854), (720, 1280), (1080, 1920), (1440, 2560), (2160, 3840)]
+    shapes = [(480, 854), (480, 640), (768, 1366), (720, 1280), (1080, 1920), (1440, 2560), (2160, 3840)]
     cpu = {}
     with mp.get_context("fork").Pool(cores) as pool:       # before CUDA is touched
         for (H, W) in shapes:
@@ -57,10 +57,10 @@ def main():
             eng.frames_features(frames)
         eng.profile(False)
         prof = eng.profile_read()
-        k1 = prof.get("k1_fused") or prof.get("k1_banded") or {"ms": sum(prof[k]["ms"] for k in ("gray", "lap", "area_h", "area_v", "area_int", "thumb") if k in prof)}
+        k1 = prof.get("k1_fused") or prof.get("k1_banded") or prof.get("k1_rows") or {"ms": sum(prof[k]["ms"] for k in ("gray", "lap", "area_h", "area_v", "area_int", "thumb") if k in prof)}
         ms = k1["ms"] / reps
         gbs = n * H * W * 3 / ms / 1e6
-        rows.append({"H": H, "W": W, "frames_per_launch": n, "path": "streaming" if "k1_fused" in prof else ("banded" if "k1_banded" in prof else "generic"),
+        rows.append({"H": H, "W": W, "frames_per_launch": n, "path": "streaming" if "k1_fused" in prof else ("banded" if "k1_banded" in prof else ("any-width" if "k1_rows" in prof else "generic")),
                      "ms_per_launch": ms, "frames_per_s": n / ms * 1e3, "GBps": gbs, "frac_measured_peak": gbs / PEAK, "frac_8TBps": gbs / 8000.0,
                      "cpu_1core_fps": cpu[(H, W)][0], "cpu_allcores_fps": cpu[(H, W)][1], "cpu_cores": cores})
         del frames

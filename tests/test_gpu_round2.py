@@ -260,3 +260,11 @@ def test_halo_frame_folded_into_the_main_launch(synth, torch, eng):
     n_separate = eng.launches - l0
     assert folded == separate == whole[160:]
     assert n_folded < n_separate
+
+
+def test_plain_c_client_of_the_abi(eng):
+    """tests/native/abi_smoke.c on the GPU: every K1 path, the 4:2:0 route, Farneback, determinism, no pinned leak."""
+    import subprocess
+    subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "avd_b200", "csrc"), "abi_smoke"])
+    out = subprocess.run([os.path.join(ROOT, "tests", "native", "abi_smoke")], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0 and "abi_smoke ok" in out.stdout, out.stdout + out.stderr

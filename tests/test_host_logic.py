@@ -102,6 +102,21 @@ def test_c_abi_exports_every_declared_symbol():
     assert "sm_100a" in out and "sm_90" not in out
 
 
+def test_plain_c_client_builds_and_fails_loudly_without_gpu():
+    """tests/native/abi_smoke.c: the C ABI is usable from plain C (gcc, no C++/CUDA/torch headers).  Without a GPU the
+    client must report AVD_ERR_NODEVICE and exit 2 -- no CPU fallback behind the boundary."""
+    import subprocess
+    csrc = os.path.join(ROOT, "avd_b200", "csrc")
+    subprocess.check_call(["make", "-s", "-C", csrc, "abi_smoke"])
+    exe = os.path.join(ROOT, "tests", "native", "abi_smoke")
+    assert os.path.exists(exe)
+    import ctypes
+    lib = ctypes.CDLL(os.path.join(csrc, "libavd.so"))
+    if lib.avd_device_count() <= 0:
+        out = subprocess.run([exe], capture_output=True, text=True)
+        assert out.returncode == 2 and "no CPU fallback" in out.stderr
+
+
 def test_no_cpu_fallback_without_gpu():
     import torch
     if torch.cuda.is_available():
