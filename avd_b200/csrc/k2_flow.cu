@@ -267,11 +267,11 @@ __global__ void __launch_bounds__(256) um_kernel(const float *__restrict__ Rall,
     const float *R1 = R0 + (size_t)PYR_PX * 5;
     float dx = 0.f, dy = 0.f;
     if (FLOWSRC == 1) {
-        const float *f = flow + (size_t)p * 2 * plane + o;
+        const float *f = flow + (size_t)blockIdx.z * 2 * plane + o;      // flow buffers are indexed by the pair's position in its chain
         dx = f[0]; dy = f[plane];
     } else if (FLOWSRC == 2) {
         constexpr int cs = S >> 1;
-        const float *cf = coarse + (size_t)p * 2 * cs * cs;
+        const float *cf = coarse + (size_t)blockIdx.z * 2 * cs * cs;
         dx = up2_sample(cf, cs, x, y); dy = up2_sample(cf + cs * cs, cs, x, y);
     }
     float m[5];
@@ -341,7 +341,7 @@ __global__ void __launch_bounds__(BCS_THREADS) box_cs_kernel(const float *__rest
     };
     const int t = threadIdx.x, px = strip * BX_COLS + t;
     const bool solver = t < BX_COLS && px < S;
-    float *fo = flow + (size_t)p * 2 * plane + px;
+    float *fo = flow + (size_t)pl * 2 * plane + px;
     double sm = 0, sq = 0;
     auto solve = [&](const double (*a)[128], int y) {
         const double g11 = a[0][8 + t], g12 = a[1][8 + t], g22 = a[2][8 + t], h1 = a[3][8 + t], h2 = a[4][8 + t];
@@ -450,6 +450,68 @@ static size_t k2_ws_bytes(int ni, int np)
     return sizeof(float) * ((size_t)ni * PYR_PX * 6 + (size_t)np * T * T * 9) + sizeof(double) * 2 * STAT_TILES_MAX * (size_t)np;
 }
 
+// Rows per box segment, per level (AVD_K2_SEG="s0,s1,s2,s3"); fixed per level -- never chosen per batch -- so that a pair's
+// flow does not depend on the batch it is computed in.
+static const int *k2_seg_rows()
+{
+    static int seg_rows[4] = {32, 24, 16, 8};
+    static bool init = false;
+    if (!init) {
+        if (const char *e = getenv("AVD_K2_SEG")) sscanf(e, "%d,%d,%d,%d", &seg_rows[0], &seg_rows[1], &seg_rows[2], &seg_rows[3]);
+        for (int &v : seg_rows) v = v < BX_MIN_SEG ? BX_MIN_SEG : v;
+        init = true;
+    }
+    return seg_rows;
+}
+
+struct ChainArgs {
+    float *R, *M, *flowA, *flowB;
+    double *tile_stats;
+    int mode;
+    bool want_stats;
+};
+
+// The flow iterations of pairs [q0, q0 + nq) of the batch on stream st: levels 3..0, per level the update matrices
+// (first launch: flow upsampled from the coarser level) and three box-sum/solve + update rounds.
+static int run_chain(avd_ctx *ctx, cudaStream_t st, const ChainArgs &A, int q0, int nq, cudaEvent_t after_first)
+{
+    // AVD_K2_LEVEL_NAMES=1: the per-kernel timing log (avd_profile_read) keeps the pyramid levels apart
+    static const bool lvl_names = getenv("AVD_K2_LEVEL_NAMES") && atoi(getenv("AVD_K2_LEVEL_NAMES"));
+    static const char *um_name[4] = {"update_matrices_L0", "update_matrices_L1", "update_matrices_L2", "update_matrices_L3"};
+    static const char *box_name[4] = {"box_solve_L0", "box_solve_L1", "box_solve_L2", "box_solve_L3"};
+    const int *seg_rows = k2_seg_rows();
+    // M and the flow buffers are indexed by the pair's position in THIS chain: the chains of a split batch are at different
+    // pyramid levels at the same time, and a level-k flow of pair p sits at p * 2 * s_k^2 -- only chain-private regions
+    // (at the finest level they coincide with the batch layout p * 2 * T^2) keep them apart
+    float *R = A.R, *M = A.M + (size_t)q0 * 5 * T * T, *cur = A.flowA + (size_t)q0 * 2 * T * T, *prev = A.flowB + (size_t)q0 * 2 * T * T;
+    double *tile_stats = A.tile_stats;
+    const int mode = A.mode;
+    const bool want_stats = A.want_stats;
+    for (int k = 3; k >= 0; k--) {
+        const int s = lvl_size(k);
+        const int seg = seg_rows[k];
+        dim3 gu((s + 31) / 32, (s + 7) / 8, nq), bu(32, 8);
+        const int tasks = bx_strips(s) * bx_segs(s, seg) * nq;
+#define UM_LAUNCH(K, SRC, FLOW, COARSE) AVD_LAUNCH(ctx, (lvl_names ? um_name[K] : "update_matrices"), st, um_kernel<K, SRC><<<gu, bu, 0, st>>>(R, FLOW, COARSE, M, mode, q0))
+#define BOX_LAUNCH(K, STATS) AVD_LAUNCH(ctx, (lvl_names ? box_name[K] : "box_solve"), st, box_cs_kernel<K, STATS><<<tasks, BCS_THREADS, 0, st>>>(M, cur, seg, nq, STATS ? tile_stats : nullptr, q0))
+#define LEVEL(K)                                                                                  \
+    {                                                                                             \
+        if (K == 3) UM_LAUNCH(K, 0, nullptr, nullptr); else UM_LAUNCH(K, 2, nullptr, prev);       \
+        if (K == 3 && after_first) AVD_CUDA(ctx, cudaEventRecord(after_first, st));               \
+        for (int it = 0; it < 3; it++) {                                                          \
+            if (K == 0 && it == 2 && want_stats) BOX_LAUNCH(K, true); else BOX_LAUNCH(K, false);  \
+            if (it < 2) UM_LAUNCH(K, 1, cur, nullptr);                                            \
+        }                                                                                         \
+    }
+        if (k == 3) LEVEL(3) else if (k == 2) LEVEL(2) else if (k == 1) LEVEL(1) else LEVEL(0)
+#undef LEVEL
+#undef BOX_LAUNCH
+#undef UM_LAUNCH
+        float *t = cur; cur = prev; prev = t;   // prev now holds this level's flow
+    }
+    return AVD_OK;
+}
+
 int k2_reserve(avd_ctx *ctx, int n_pairs)
 {
     if (n_pairs <= 0) return AVD_OK;
@@ -499,54 +561,28 @@ int k2_flow(avd_ctx *ctx, const uint8_t *d_prev, const uint8_t *d_next, size_t p
             int s = lvl_size(k);
             AVD_LAUNCH(ctx, "polyexp", st, polyexp_kernel<<<dim3(s / PE_ROWS, ni), (s + 31) / 32 * 32, 3 * PE_ROWS * (s + 2 * PE_HALO) * sizeof(float), st>>>(pyr, R, k));
         }
-        float *cur = flowA, *prev = flowB;
-        // Flow iterations: um_kernel<K,.> + box_cs_kernel<K,.> per level, 3 iterations each.
-        // Rows per box segment, per level (AVD_K2_SEG="s0,s1,s2,s3"); fixed per level -- never chosen per batch -- so that a
-        // pair's flow does not depend on the batch it is computed in.  AVD_K2_SB="b0,b1,b2,b3": pairs per sub-batch at each
-        // level (0 = the whole batch; a sub-batch reuses the same M storage -- measured slower on B200 at every size tried,
-        // profiles/r02_k2_notes.md, kept as a tuning knob).
-        static int seg_rows[4] = {32, 24, 16, 8};
-        static int sub_batch[4] = {0, 0, 0, 0};
-        static bool seg_init = false;
-        if (!seg_init) {
-            if (const char *e = getenv("AVD_K2_SEG")) sscanf(e, "%d,%d,%d,%d", &seg_rows[0], &seg_rows[1], &seg_rows[2], &seg_rows[3]);
-            if (const char *e = getenv("AVD_K2_SB")) sscanf(e, "%d,%d,%d,%d", &sub_batch[0], &sub_batch[1], &sub_batch[2], &sub_batch[3]);
-            for (int &v : seg_rows) v = v < BX_MIN_SEG ? BX_MIN_SEG : v;
-            seg_init = true;
-        }
-        const bool want_stats = d_rec_first != nullptr;
-        // AVD_K2_LEVEL_NAMES=1: the per-kernel timing log (avd_profile_read) keeps the pyramid levels apart
-        static const bool lvl_names = getenv("AVD_K2_LEVEL_NAMES") && atoi(getenv("AVD_K2_LEVEL_NAMES"));
-        static const char *um_name[4] = {"update_matrices_L0", "update_matrices_L1", "update_matrices_L2", "update_matrices_L3"};
-        static const char *box_name[4] = {"box_solve_L0", "box_solve_L1", "box_solve_L2", "box_solve_L3"};
-        for (int k = 3; k >= 0; k--) {
-            const int s = lvl_size(k);
-            const int SB = sub_batch[k] > 0 && sub_batch[k] < np ? sub_batch[k] : np;
-            const int seg = seg_rows[k];
-            for (int q0 = 0; q0 < np; q0 += SB) {
-                const int nq = np - q0 < SB ? np - q0 : SB;
-                dim3 gu((s + 31) / 32, (s + 7) / 8, nq), bu(32, 8);
-                const int tasks = bx_strips(s) * bx_segs(s, seg) * nq;
-#define UM_LAUNCH(K, SRC, FLOW, COARSE) AVD_LAUNCH(ctx, (lvl_names ? um_name[K] : "update_matrices"), st, um_kernel<K, SRC><<<gu, bu, 0, st>>>(R, FLOW, COARSE, M, mode, q0))
-#define BOX_LAUNCH(K, STATS) AVD_LAUNCH(ctx, (lvl_names ? box_name[K] : "box_solve"), st, box_cs_kernel<K, STATS><<<tasks, BCS_THREADS, 0, st>>>(M, cur, seg, nq, STATS ? tile_stats : nullptr, q0))
-#define LEVEL(K)                                                                                  \
-    {                                                                                             \
-        if (K == 3) UM_LAUNCH(K, 0, nullptr, nullptr); else UM_LAUNCH(K, 2, nullptr, prev);       \
-        for (int it = 0; it < 3; it++) {                                                          \
-            if (K == 0 && it == 2 && want_stats) BOX_LAUNCH(K, true); else BOX_LAUNCH(K, false);  \
-            if (it < 2) UM_LAUNCH(K, 1, cur, nullptr);                                            \
-        }                                                                                         \
-    }
-                if (k == 3) LEVEL(3) else if (k == 2) LEVEL(2) else if (k == 1) LEVEL(1) else LEVEL(0)
-#undef LEVEL
-#undef BOX_LAUNCH
-#undef UM_LAUNCH
+        // Flow iterations (run_chain): um_kernel<K,.> + box_cs_kernel<K,.> per level, 3 iterations each.
+        // AVD_K2_SPLIT=2: the pairs of the batch are split into two halves whose chains run on two streams, the second one
+        // launch behind the first, so that the memory-bound update_matrices of one half shares the SMs with the issue-bound
+        // box_solve of the other.  A pair's arithmetic does not depend on which half it is in.
+        static const int split = getenv("AVD_K2_SPLIT") ? atoi(getenv("AVD_K2_SPLIT")) : 2;
+        ChainArgs A{R, M, flowA, flowB, tile_stats, mode, d_rec_first != nullptr};
+        if (split >= 2 && np >= 32) {      // measured: 119 pairs 1.52 -> 1.45 ms, 80: 1.08 -> 1.03, 40: 0.64 -> 0.63, 16: slower
+            if (!ctx->k2_side) {
+                AVD_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->k2_side, cudaStreamNonBlocking));
+                for (int i = 0; i < 2; i++) AVD_CUDA(ctx, cudaEventCreateWithFlags(&ctx->k2_ev[i], cudaEventDisableTiming));
             }
-            float *t = cur; cur = prev; prev = t;   // prev now holds this level's flow
-        }
+            const int h = (np + 1) / 2;
+            if ((rc = run_chain(ctx, st, A, 0, h, ctx->k2_ev[0]))) return rc;          // k2_ev[0]: recorded behind the first launch
+            AVD_CUDA(ctx, cudaStreamWaitEvent(ctx->k2_side, ctx->k2_ev[0], 0));
+            if ((rc = run_chain(ctx, ctx->k2_side, A, h, np - h, nullptr))) return rc;
+            AVD_CUDA(ctx, cudaEventRecord(ctx->k2_ev[1], ctx->k2_side));
+            AVD_CUDA(ctx, cudaStreamWaitEvent(st, ctx->k2_ev[1], 0));
+        } else if ((rc = run_chain(ctx, st, A, 0, np, nullptr))) return rc;
+        float *prev = flowB;                       // levels 3..0 write flowA, flowB, flowA, flowB: the finest flow ends in flowB
         if (d_rec_first) {
             // chain: pair p0+j -> record of its "next" image
-            AVD_LAUNCH(ctx, "magstats", st, magstats_finalize_kernel<<<(np + 127) / 128, 128, 0, st>>>(tile_stats, bx_strips(T) * bx_segs(T, seg_rows[0]), d_rec_first + p0, np));
+            AVD_LAUNCH(ctx, "magstats", st, magstats_finalize_kernel<<<(np + 127) / 128, 128, 0, st>>>(tile_stats, bx_strips(T) * bx_segs(T, k2_seg_rows()[0]), d_rec_first + p0, np));
         }
         if (d_flow_out) {
             size_t total = (size_t)np * T * T;
