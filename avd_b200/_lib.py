@@ -20,7 +20,7 @@ SYMBOLS = ["avd_version", "avd_device_count", "avd_create", "avd_destroy", "avd_
            "avd_host_alloc", "avd_host_free", "avd_frames_features", "avd_flow_stats", "avd_flow_fields",
            "avd_gray", "avd_analyze_host", "avd_launch_count", "avd_set_k1_mode", "avd_profile_enable",
            "avd_profile_read", "avd_shape_plan", "avd_score_clips", "avd_audio_windows", "avd_ws_generation",
-           "avd_host_alloc_count", "avd_yuv420_to_bgr", "avd_analyze_host_yuv420"]
+           "avd_host_alloc_count", "avd_yuv420_to_bgr", "avd_analyze_host_yuv420", "avd_check_guards"]
 
 
 class AvdError(RuntimeError):
@@ -63,6 +63,7 @@ def load():
     L.avd_audio_windows.argtypes = [vp, vp, C.c_longlong, C.c_int, vp, vp]; L.avd_audio_windows.restype = C.c_int
     L.avd_ws_generation.argtypes = [vp]; L.avd_ws_generation.restype = C.c_uint64
     L.avd_host_alloc_count.argtypes = [vp]; L.avd_host_alloc_count.restype = sz
+    L.avd_check_guards.argtypes = [vp]; L.avd_check_guards.restype = C.c_longlong
     L.avd_yuv420_to_bgr.argtypes = [vp, u8p, sz, C.c_int, C.c_int, C.c_int, C.c_int, u8p, sz, sz, vp]; L.avd_yuv420_to_bgr.restype = C.c_int
     L.avd_analyze_host_yuv420.argtypes = [vp, C.POINTER(vp), C.c_int, C.c_int, C.c_int, C.c_int, vp]; L.avd_analyze_host_yuv420.restype = C.c_int
     _lib = L

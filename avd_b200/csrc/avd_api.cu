@@ -122,22 +122,45 @@ int avd_get_tables(avd_ctx *ctx, int H, int W, const ShapeTables **dev, const Sh
     return AVD_OK;
 }
 
+// Grow-only device buffers of the library.  Every buffer sits between two guard zones filled with a canary pattern;
+// avd_check_guards() verifies them (compute-sanitizer is not available on every pool: an out-of-bounds WRITE by any kernel
+// into the neighbourhood of a workspace shows up here).
+constexpr size_t AVD_GUARD = 256;            // bytes on each side; keeps the 256-byte alignment of cudaMalloc
+constexpr int AVD_CANARY = 0xA5;
+
+static void guarded_free(avd_ctx *ctx, void *user)
+{
+    for (size_t i = 0; i < ctx->guarded.size(); i++)
+        if (ctx->guarded[i].user == user) {
+            cudaFree(ctx->guarded[i].base);
+            ctx->guarded.erase(ctx->guarded.begin() + i);
+            return;
+        }
+    cudaFree(user);
+}
+
 int avd_ensure(avd_ctx *ctx, void **p, size_t *cap, size_t need)
 {
     if (*cap >= need) return AVD_OK;
-    if (*p) { cudaFree(*p); *p = nullptr; *cap = 0; }
+    if (*p) { guarded_free(ctx, *p); *p = nullptr; *cap = 0; }
     ctx->ws_generation++;            // cached CUDA graphs hold the old address: callers key their caches on this
     size_t want = need + need / 8;
-    if (cudaMalloc(p, want) != cudaSuccess) {
+    want = (want + 255) & ~(size_t)255;
+    void *base = nullptr;
+    if (cudaMalloc(&base, want + 2 * AVD_GUARD) != cudaSuccess) {
         cudaGetLastError();
-        if (cudaMalloc(p, need) != cudaSuccess) {
+        want = (need + 255) & ~(size_t)255;
+        if (cudaMalloc(&base, want + 2 * AVD_GUARD) != cudaSuccess) {
             cudaGetLastError();
             ctx->err = "cudaMalloc of " + std::to_string(need) + " bytes failed";
             return AVD_ERR_NOMEM;
         }
-        want = need;
     }
+    cudaMemset(base, AVD_CANARY, AVD_GUARD);
+    cudaMemset((char *)base + AVD_GUARD + want, AVD_CANARY, AVD_GUARD);
+    *p = (char *)base + AVD_GUARD;
     *cap = want;
+    ctx->guarded.push_back({base, *p, want});
     return AVD_OK;
 }
 
@@ -200,8 +223,8 @@ void avd_destroy(avd_ctx *ctx)
     cudaSetDevice(ctx->device);
     cudaDeviceSynchronize();
     for (auto &kv : ctx->tables) cudaFree(kv.second);
-    cudaFree(ctx->gray); cudaFree(ctx->area_rows); cudaFree(ctx->k2_ws); cudaFree(ctx->ring); cudaFree(ctx->bgr_slot);
-    cudaFree(ctx->thumbs); cudaFree(ctx->recs); cudaFree(ctx->area32); cudaFree(ctx->fixlist); cudaFree(ctx->k3_ws); cudaFree(ctx->k4_ws);
+    for (auto &g : ctx->guarded) cudaFree(g.base);          // every grow-only workspace (avd_ensure)
+    ctx->guarded.clear();
     for (void *h : ctx->host_allocs) cudaFreeHost(h);
     ctx->host_allocs.clear();
     for (int i = 0; i < 4; i++) { cudaEventDestroy(ctx->ev_copied[i]); cudaEventDestroy(ctx->ev_free[i]); }
@@ -239,6 +262,31 @@ void avd_host_free(avd_ctx *ctx, void *p)
 
 uint64_t avd_launch_count(const avd_ctx *ctx) { return ctx ? ctx->launches : 0; }
 uint64_t avd_ws_generation(const avd_ctx *ctx) { return ctx ? ctx->ws_generation : 0; }
+
+// Number of corrupted guard bytes around the library's device buffers (0 = intact), or a negative status.
+long long avd_check_guards(avd_ctx *ctx)
+{
+    if (!ctx) return AVD_ERR_ARG;
+    if (cudaSetDevice(ctx->device) != cudaSuccess || cudaDeviceSynchronize() != cudaSuccess) {
+        ctx->err = std::string("avd_check_guards: ") + cudaGetErrorString(cudaGetLastError());
+        return AVD_ERR_CUDA;
+    }
+    long long bad = 0;
+    unsigned char h[2 * AVD_GUARD];
+    for (size_t i = 0; i < ctx->guarded.size(); i++) {
+        const auto &g = ctx->guarded[i];
+        if (cudaMemcpy(h, g.base, AVD_GUARD, cudaMemcpyDeviceToHost) != cudaSuccess ||
+            cudaMemcpy(h + AVD_GUARD, (char *)g.base + AVD_GUARD + g.cap, AVD_GUARD, cudaMemcpyDeviceToHost) != cudaSuccess) {
+            cudaGetLastError();
+            return AVD_ERR_CUDA;
+        }
+        long long b = 0;
+        for (size_t k = 0; k < 2 * AVD_GUARD; k++) b += h[k] != AVD_CANARY;
+        if (b) ctx->err = "guard zone of workspace #" + std::to_string(i) + " (" + std::to_string(g.cap) + " bytes) overwritten: " + std::to_string(b) + " bytes";
+        bad += b;
+    }
+    return bad;
+}
 size_t avd_host_alloc_count(const avd_ctx *ctx) { return ctx ? ctx->host_allocs.size() : 0; }
 
 int avd_profile_enable(avd_ctx *ctx, int on)

@@ -56,6 +56,8 @@ struct avd_ctx {
     std::string err;
     uint64_t launches = 0;
     uint64_t ws_generation = 0;                            // bumped whenever a grow-only device buffer moves (avd_ensure)
+    struct Guarded { void *base, *user; size_t cap; };
+    std::vector<Guarded> guarded;                          // grow-only device buffers with their guard zones (avd_ensure)
     std::set<void *> host_allocs;                          // avd_host_alloc regions not yet freed (released by avd_destroy)
     int k1_mode = 0;
     std::map<std::pair<int, int>, ShapeTables *> tables;   // device pointers

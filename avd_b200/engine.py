@@ -71,6 +71,14 @@ class Engine:
         """Bumped by the library whenever one of its scratch buffers moves (include/avd.h: avd_ws_generation)."""
         return int(self.L.avd_ws_generation(self.h))
 
+    def check_guards(self) -> int:
+        """Corrupted guard bytes around the library's device workspaces (0 = intact); raises on a CUDA error."""
+        with self._lock:
+            n = int(self.L.avd_check_guards(self.h))
+        if n < 0:
+            self._check(n, "avd_check_guards")
+        return n
+
     def set_k1_mode(self, mode: int):
         self._check(self.L.avd_set_k1_mode(self.h, int(mode)), "avd_set_k1_mode")
 

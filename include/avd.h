@@ -198,6 +198,10 @@ uint64_t avd_launch_count(const avd_ctx *ctx);
  * value differs from the one it saw at capture time (the graph holds the old addresses). */
 uint64_t avd_ws_generation(const avd_ctx *ctx);
 
+/* Every device buffer the library owns sits between two 256-byte guard zones filled with a canary.  Returns the number of
+ * guard bytes that no longer hold it (0 = no kernel wrote outside a workspace), or a negative avd_status.  Synchronises. */
+long long avd_check_guards(avd_ctx *ctx);
+
 /* Per-kernel device timing for bench.py: when enabled, every launch is bracketed by CUDA events on its
  * stream.  avd_profile_read synchronises, writes JSON {"kernel": {"ms": total, "launches": n}, ...} to buf
  * and clears the log. */

@@ -59,6 +59,7 @@ int main(void)
     bad |= run_shape(ctx, 720, 1280, 4, 1);     /* 4:2:0 upload + device colour conversion */
     bad |= run_shape(ctx, 66, 34, 3, 1);        /* 4:2:0, byte kernel, tiny */
     if (avd_host_alloc_count(ctx) != 0) { fprintf(stderr, "pinned regions leaked\n"); bad = 1; }
+    if (avd_check_guards(ctx) != 0) { fprintf(stderr, "guard zones: %s\n", avd_last_error(ctx)); bad = 1; }
     avd_destroy(ctx);
     printf(bad ? "FAILED\n" : "abi_smoke ok\n");
     return bad;

@@ -31,6 +31,7 @@ def eng(torch):
     from avd_b200.engine import Engine
     e = Engine(0)
     yield e
+    assert e.check_guards() == 0, "a kernel wrote outside one of the library's device workspaces"
     e.close()
 
 

@@ -31,6 +31,7 @@ def eng(torch):
     from avd_b200.engine import Engine
     e = Engine(0)
     yield e
+    assert e.check_guards() == 0, "a kernel wrote outside one of the library's device workspaces"
     e.close()
 
 
@@ -268,3 +269,68 @@ def test_plain_c_client_of_the_abi(eng):
     subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "avd_b200", "csrc"), "abi_smoke"])
     out = subprocess.run([os.path.join(ROOT, "tests", "native", "abi_smoke")], capture_output=True, text=True, timeout=300)
     assert out.returncode == 0 and "abi_smoke ok" in out.stdout, out.stdout + out.stderr
+
+
+def test_split_flow_chains_equal_single_chain_and_replay_in_a_graph(synth, torch, monkeypatch):
+    """K2 runs the flow iterations of a batch of >= 32 pairs as two chains on two streams (AVD_K2_SPLIT, default 2).
+    The records must be those of the single-chain run, byte for byte, also when the fork/join is captured in a CUDA graph,
+    and a pair's statistics must not depend on the batch it is computed in."""
+    import subprocess, sys, textwrap
+    code = textwrap.dedent("""
+        import sys, numpy as np, torch
+        sys.path.insert(0, %r)
+        import avd_b200.synth as synth
+        from avd_b200.engine import Engine
+        eng = Engine(0)
+        clip = synth.Clip(90, 360, 640, seed=88, events=True, pan=2)
+        fr = torch.from_numpy(np.stack([clip[i] for i in range(0, 90, 2)])).cuda()       # 45 samples, 44 pairs
+        a = eng.analyze_device(fr).cpu().numpy().tobytes()
+        g1 = eng.analyze_device_graph(fr).cpu().numpy().tobytes()
+        g2 = eng.analyze_device_graph(fr).cpu().numpy().tobytes()
+        small = eng.analyze_device(fr[:20]).cpu().numpy().tobytes()                       # 19 pairs: one chain
+        assert a == g1 == g2 and small == a[:20 * 160]
+        sys.stdout.write(__import__("hashlib").sha256(a).hexdigest())
+    """ % ROOT)
+    outs = []
+    for split in ("1", "2"):
+        env = dict(os.environ, AVD_K2_SPLIT=split)
+        r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, timeout=600)
+        assert r.returncode == 0, r.stdout + r.stderr
+        outs.append(r.stdout.strip())
+    assert outs[0] == outs[1] and len(outs[0]) == 64
+
+
+@pytest.mark.parametrize("H,W", [(1080, 1920), (720, 1280), (480, 854), (272, 480), (33, 35), (641, 1283)])
+def test_kernels_write_only_inside_caller_buffers(synth, torch, eng, H, W):
+    """compute-sanitizer is closed on the GPU pool, so out-of-bounds WRITES are hunted with canaries: every output buffer of
+    the device entry points (records, thumbnails, 32x32 means, BGR frames of K0) sits inside a larger allocation filled with a
+    pattern; after the calls the surroundings must be untouched, and the library's own workspaces are guarded the same way
+    (avd_check_guards).  Covers the streaming, banded and any-width per-frame kernels, K0 (both kernels) and K2."""
+    import ctypes as C
+    n, PAD = 5, 4096
+    fr = torch.from_numpy(synth.noise_frames(n, H, W, 23)).cuda()
+
+    def padded(nbytes):
+        buf = torch.full((nbytes + 2 * PAD,), 0xA5, dtype=torch.uint8, device="cuda")
+        return buf, buf[PAD:PAD + nbytes]
+
+    rec_b, rec = padded(n * 160)
+    th_b, th = padded(n * 320 * 320)
+    ar_b, ar = padded(n * 1024)
+    L, h = eng.L, eng.h
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    with eng._lock:
+        eng._check(L.avd_frames_features(h, C.c_void_p(fr.data_ptr()), n, H, W, 3 * W, 3 * W * H, None, C.c_void_p(rec.data_ptr()),
+                                         C.c_void_p(th.data_ptr()), C.c_void_p(ar.data_ptr()), st), "avd_frames_features")
+        eng._check(L.avd_flow_stats(h, C.c_void_p(th.data_ptr()), n, None, C.c_void_p(rec.data_ptr()), st), "avd_flow_stats")
+    He, We = H & ~1, W & ~1
+    yuv = torch.randint(0, 256, (n, He * We * 3 // 2), dtype=torch.uint8, device="cuda")
+    pitch = 3 * We + (16 - (3 * We) % 16) % 16
+    bg_b, bg = padded(n * He * pitch)
+    with eng._lock:
+        eng._check(L.avd_yuv420_to_bgr(h, C.c_void_p(yuv.data_ptr()), yuv.stride(0), n, He, We, 0, C.c_void_p(bg.data_ptr()), pitch, He * pitch, st),
+                   "avd_yuv420_to_bgr")
+    torch.cuda.synchronize()
+    for name, b, nbytes in (("records", rec_b, n * 160), ("thumbnails", th_b, n * 102400), ("area32", ar_b, n * 1024), ("bgr", bg_b, n * He * pitch)):
+        assert bool((b[:PAD] == 0xA5).all()) and bool((b[PAD + nbytes:] == 0xA5).all()), (name, H, W)
+    assert eng.check_guards() == 0
