@@ -207,11 +207,20 @@ def sub_config2(eng, rank, world, dev, barrier, reduce_max, reduce_min):
     cpu = cv_body.run_chunk(local[:m], halo, collect_ints=True)
     keys = ("textures", "flow_means", "flow_vars", "dup", "timeline", "hash_words", "hams", "lap_sums")
     mine = parity.records_vs_cpu_body(full[lo:lo + m], dict(zip(keys, cpu)), H4 * W4, first_has_prev=halo is not None)
-    ok = reduce_min(1.0 if (mine["ok"] and parity.chain_consistent(full)) else 0.0) > 0.5
+    # (iii) every sample of this rank's shard, and on rank 0 the returned dict, against the reference's own analyze() run on the
+    # whole clip (tests/golden/golden_4k_full.json)
+    gp = os.path.join(ROOT, "tests", "golden", "golden_4k_full.json")
+    gold, vs_gold, dict_ok = (json.load(open(gp)) if os.path.exists(gp) else None), None, None
+    if gold is not None:
+        vs_gold = parity.records_vs_golden_range(full[lo:hi], gold, lo, first_has_prev=halo is not None)
+        dict_ok = parity.video_dict_vs_golden(res, gold["result"])
+    ok = reduce_min(1.0 if (mine["ok"] and parity.chain_consistent(full) and (vs_gold is None or (vs_gold["ok"] and dict_ok))) else 0.0) > 0.5
     eng.free_pinned(pin)
     return {"workload": "configs[2]: 4K 60fps 30s clip, 60 sampled frames (1.49 GB BGR) frame-chunk sharded, 1-sample halo, all-gather of records",
             "value": n_total * iters / dt, "unit": "frames/s", "ms_per_pass": 1e3 * dt / iters, "samples_per_rank": hi - lo,
-            "parity": {"ok": bool(ok), "rank0": mine, "checked": "per rank: first 2 samples after the shard boundary vs the CPU body (ints exact, floats in tolerance); gathered Hamming chain consistent"},
+            "parity": {"ok": bool(ok), "rank0_first2_vs_cpu_body": mine, "rank0_shard_vs_reference_golden": vs_gold, "result_dict_vs_reference_golden": dict_ok,
+                       "checked": "every rank: all samples of its shard vs the reference's analyze() golden of the whole clip (ints exact, flow in tolerance) and the "
+                                  "assembled result dict vs the reference's; first 2 samples after the shard boundary vs the CPU body; gathered Hamming chain consistent"},
             "ai_score": None if res is None else float(np.mean(res["timeline"]))}
 
 
@@ -256,12 +265,23 @@ def sub_config3(eng, rank, world, barrier, reduce_max, reduce_min, clips_per_ran
         ok &= (t["ok"] and d <= 1e-3 and ref_f["result"]["label"] == out[ci]["fusion"]["result"]["label"]
                and v["summary"]["dup_density"] == ref_v["summary"]["dup_density"]
                and abs(v["summary"]["texture_var"] - ref_v["summary"]["texture_var"]) <= 1e-9 * abs(ref_v["summary"]["texture_var"]))
+    # every clip of this rank against the reference's analyze() + fuse() run on the same clip (tests/golden/golden_clips256.json)
+    gp = os.path.join(ROOT, "tests", "golden", "golden_clips256.json")
+    n_gold = 0
+    if os.path.exists(gp):
+        gold = {c["seed"]: c for c in json.load(open(gp))["clips"]}
+        for ci, sd in enumerate(seeds):
+            if sd in gold:
+                n_gold += 1
+                ok &= parity.video_dict_vs_golden(out[ci]["video"], gold[sd]["video"]) and parity.fused_vs_golden(out[ci]["fusion"], gold[sd]["fused"])
     ok = reduce_min(1.0 if ok else 0.0) > 0.5
     eng.free_pinned(pin)
     return {"workload": f"configs[3]: {clips_per_rank * world} x 720p 5s clips (10 samples each) clip-sharded, {clips_per_rank} clips per GPU, frames -> fused verdicts (K1+K2+K3)",
             "value": clips_per_rank * 10 * world * iters / dt, "unit": "frames/s", "ms_per_pass": 1e3 * dt / iters,
             "clips_per_s": clips_per_rank * world * iters / dt,
-            "parity": {"ok": bool(ok), "score_delta_max_rank0": worst, "checked": "2 clips per rank vs the CPU body + host fuse: timeline in tolerance, dup_density equal, texture_var 1e-9, pre-rounding score <= 1e-3, label equal"}}
+            "parity": {"ok": bool(ok), "score_delta_max_rank0": worst, "clips_vs_reference_golden_rank0": n_gold,
+                       "checked": "every clip vs the reference's analyze()+fuse() golden (timeline, summary, label, peaks, binned timeline, rounded scores); "
+                                  "2 clips per rank vs the CPU body + host fuse: timeline in tolerance, dup_density equal, texture_var 1e-9, pre-rounding score <= 1e-3, label equal"}}
 
 
 def main():

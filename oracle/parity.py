@@ -95,3 +95,37 @@ def chain_consistent(recs: np.ndarray) -> bool:
         if int(recs["ham_prev"][i]) != d or not (int(recs["flags"][i]) & REC_HAS_PREV) or not (int(recs["flags"][i]) & REC_HAS_FLOW):
             return False
     return len(recs) == 0 or int(recs["ham_prev"][0]) == -1
+
+
+def records_vs_golden_range(recs: np.ndarray, g: dict, lo: int, first_has_prev: bool) -> dict:
+    """Records of samples [lo, lo + len(recs)) of a clip against the reference's golden for the whole clip (any clip golden made
+    by tests/golden/make_golden_*.py): integer fields exact, flow statistics in tolerance."""
+    n = len(recs)
+    hi = lo + n
+    int_exact = ([r.tolist() for r in recs["hash"]] == g["hash_words"][lo:hi]
+                 and [int(x) for x in recs["lap_sum"]] == g["lap_sum"][lo:hi] and [int(x) for x in recs["lap_sumsq"]] == g["lap_sumsq"][lo:hi])
+    k0 = 0 if (first_has_prev and lo > 0) else 1                      # first record of the range that has a predecessor
+    int_exact &= [int(x) for x in recs["ham_prev"][k0:]] == g["ham"][lo + k0 - 1:hi - 1]
+    ref = g["flow_stats"][lo + k0 - 1:hi - 1]
+    f_ok, f_rel, f_abs = _flow_check(recs["flow_mean"][k0:], recs["flow_var"][k0:], [m for m, _ in ref], [v for _, v in ref])
+    return {"samples": n, "int_exact": bool(int_exact), "flow_max_rel": f_rel, "flow_static_max_abs": f_abs, "ok": bool(int_exact and f_ok)}
+
+
+def video_dict_vs_golden(v: dict, ref: dict) -> bool:
+    """What video.analyze returns against the reference's dict for the same clip."""
+    if len(v["timeline"]) != len(ref["timeline"]) or not timeline_vs_cpu(v["timeline"], ref["timeline"])["ok"]:
+        return False
+    a, b = v["summary"], ref["summary"]
+    if any(a[k] != b[k] for k in ("dup_density", "scene_change_rate", "w", "h", "fps")):
+        return False
+    return all(abs(a[k] - b[k]) <= RTOL * abs(b[k]) + ATOL_STATIC for k in ("flow_mean", "flow_var")) and abs(a["texture_var"] - b["texture_var"]) <= 1e-9 * abs(b["texture_var"]) + 1e-12
+
+
+def fused_vs_golden(f: dict, ref: dict) -> bool:
+    """fusion.fuse output against the reference's: label, peaks, binned timeline; ai_score / confidence may differ by one unit
+    in the last rounded digit only when the pre-rounding value sits on a x.xx5 boundary."""
+    return (f["result"]["label"] == ref["result"]["label"] and f["peaks"] == ref["peaks"]
+            and abs(f["result"]["ai_score"] - ref["result"]["ai_score"]) <= 0.01 + 1e-12
+            and abs(f["result"]["confidence"] - ref["result"]["confidence"]) <= 0.01 + 1e-12
+            and len(f["timeline_binned"]) == len(ref["timeline_binned"])
+            and all(abs(x - y) <= 1e-3 for x, y in zip(f["timeline_binned"], ref["timeline_binned"])))

@@ -334,3 +334,43 @@ def test_kernels_write_only_inside_caller_buffers(synth, torch, eng, H, W):
     for name, b, nbytes in (("records", rec_b, n * 160), ("thumbnails", th_b, n * 102400), ("area32", ar_b, n * 1024), ("bgr", bg_b, n * He * pitch)):
         assert bool((b[:PAD] == 0xA5).all()) and bool((b[PAD + nbytes:] == 0xA5).all()), (name, H, W)
     assert eng.check_guards() == 0
+
+
+def test_config2_4k_head_vs_reference_golden(synth, eng):
+    """BASELINE configs[2] geometry at full frame size: the first 12 samples of the 4K 60 fps seed-2 clip against the
+    reference's own analyze() run on the whole clip (tests/golden/golden_4k_full.json): integers exact, flow in tolerance."""
+    from oracle import parity
+    with open(os.path.join(ROOT, "tests", "golden", "golden_4k_full.json")) as f:
+        g = json.load(f)
+    clip = synth.Clip(g["n_frames"], g["H"], g["W"], g["seed"], fps=g["fps"])
+    frames = np.stack([clip[i * g["step"]] for i in range(12)])
+    recs = eng.analyze_host(frames)
+    v = parity.records_vs_golden_range(recs, g, 0, first_has_prev=False)
+    assert v["ok"] and v["int_exact"], v
+    # a shard that starts in the middle of the clip, seeded by its halo sample (what rank r > 0 computes)
+    recs2 = eng.analyze_host(frames[4:])
+    v2 = parity.records_vs_golden_range(recs2[1:], g, 5, first_has_prev=True)
+    assert v2["ok"], v2
+
+
+def test_config3_clip_batch_vs_reference_golden(synth, eng):
+    """BASELINE configs[3]: 16 of the 256 short 720p clips, frames -> fused verdicts on the device (K1 + K2 + K3), against the
+    reference's analyze() + fuse() dicts for the same clips (tests/golden/golden_clips256.json)."""
+    from concurrent.futures import ThreadPoolExecutor
+    from avd_b200 import fusion, hints, scoring
+    from oracle import parity
+    with open(os.path.join(ROOT, "tests", "golden", "golden_clips256.json")) as f:
+        g = json.load(f)
+    gold = {c["seed"]: c for c in g["clips"]}
+    seeds = list(range(1000, 1256, 16))
+    with ThreadPoolExecutor(8) as ex:
+        clips = list(ex.map(lambda sd: synth.Clip(g["n_frames"], g["H"], g["W"], sd, fps=g["fps"]).sampled(g["step"]), seeds))
+    meta = {"fps": 30.0, "width": 1280, "height": 720, "duration": 5.0, "bit_rate": g["hints_meta_bit_rate"]}
+    hn = hints.compute_hints(dict(meta), "")
+    assert hn == g["hints"]
+    out = scoring.score_clip_batch(eng, clips, [dict(meta) for _ in clips], audios=[fusion.neutral_audio(5) for _ in clips],
+                                   hints=[hn for _ in clips], with_raw=True)
+    for sd, c, o in zip(seeds, clips, out):
+        ref = gold[sd]
+        assert parity.video_dict_vs_golden(o["video"], ref["video"]), (sd, o["video"], ref["video"])
+        assert parity.fused_vs_golden(o["fusion"], ref["fused"]), (sd, o["fusion"], ref["fused"])

@@ -139,3 +139,19 @@ def test_oracle_reproduces_full_1080p_reference_golden_slice(oracle, synth):
             m, v = g["flow_stats"][i - 1]
             assert r["ham"] == g["ham"][i - 1]
             assert close(r["flow_mean"], m, atol=flow_atol(m)) and close(r["flow_var"], v, atol=flow_atol(m)), (i, r["flow_mean"], m)
+
+
+def test_oracle_reproduces_configs3_clip_golden(oracle, synth):
+    """One of the 256 configs[3] clips: the oracle's records -> tail -> fuse against the reference's dicts
+    (tests/golden/golden_clips256.json)."""
+    from oracle import parity
+    with open(os.path.join(ROOT, "tests", "golden", "golden_clips256.json")) as f:
+        g = json.load(f)
+    ref = next(c for c in g["clips"] if c["seed"] == 1003)
+    frames = synth.Clip(g["n_frames"], g["H"], g["W"], 1003, fps=g["fps"]).sampled(g["step"])
+    recs = oracle.frames_features(frames)
+    assert recs[0]["lap_sum"] == ref["lap_sum0"] and recs[0]["hash"].tolist() == ref["hash0"]
+    v = oracle.video_result(recs, g["H"], g["W"], g["fps"], 5.0)
+    assert parity.video_dict_vs_golden(v, ref["video"])
+    f = oracle.fuse({"scores": {}, "flags_audio": {}, "timeline": [0.5] * 5}, v, g["hints"])
+    assert parity.fused_vs_golden(f, ref["fused"])
