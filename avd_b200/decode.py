@@ -1,9 +1,8 @@
 """Host decode for the drop-in `video.analyze(path, meta)` -- the reference's grab/retrieve loop (video.py:11,27-34).
 
-Two frame sources with one interface (`open_source(path)` -> object with `fmt`, `width`, `height`, `fps`, `frame_count`,
-`grab()`, `retrieve_into(dst)`, `release()`):
+`video.analyze` has two frame sources: `cv2.VideoCapture`, exactly what the reference uses (`retrieve()` returns packed BGR,
+3 bytes / pixel), and, defined here:
 
-* `Cv2Source`  -- `cv2.VideoCapture`, exactly what the reference uses: `retrieve()` returns packed BGR (3 bytes / pixel).
 * `LibavSource` -- the same FFmpeg libraries OpenCV's backend decodes with (the copies bundled in the opencv wheel, or the
   system's), driven directly through their C API with ctypes, so that the decoder's native planar 4:2:0 picture can be
   handed on *before* the colour conversion `retrieve()` would do on the host.  The GPU then performs that conversion
@@ -11,7 +10,7 @@ Two frame sources with one interface (`open_source(path)` -> object with `fmt`, 
   installed the same planes are available from `av.VideoFrame.planes`; this image has no PyAV, hence the ctypes shim.
 
 `LibavSource` is used only when it is provably equivalent: 8-bit yuv420p / yuvj420p, even width and height, no rotation
-metadata (OpenCV auto-rotates), libavformat major >= 60 (struct offsets below).  Anything else -> `Cv2Source`.  Both feed the
+metadata (OpenCV auto-rotates), libavformat major >= 60 (struct offsets below).  Anything else -> `cv2.VideoCapture`.  Both feed the
 same device path; this is a choice of input format, not a CPU fallback.
 """
 from __future__ import annotations
@@ -31,35 +30,6 @@ AVERROR_EAGAIN = -11
 
 class DecodeUnavailable(RuntimeError):
     pass
-
-
-# ---- cv2 ---------------------------------------------------------------------------------------------------
-class Cv2Source:
-    fmt = "bgr"
-
-    def __init__(self, path: str):
-        import cv2
-        self.cv2 = cv2
-        self.cap = cv2.VideoCapture(path)
-        self.opened = self.cap.isOpened()
-        self.fps = self.cap.get(cv2.CAP_PROP_FPS) if self.opened else 0.0
-        self.width = int(self.cap.get(cv2.CAP_PROP_FRAME_WIDTH) or 0) if self.opened else 0
-        self.height = int(self.cap.get(cv2.CAP_PROP_FRAME_HEIGHT) or 0) if self.opened else 0
-        self.frame_count = self.cap.get(cv2.CAP_PROP_FRAME_COUNT) if self.opened else 0.0
-        self._frame = None
-
-    def grab(self) -> bool:
-        return self.cap.grab()
-
-    def retrieve(self):
-        """(ok, frame) -- packed BGR (H, W, 3)."""
-        return self.cap.retrieve()
-
-    def frame_nbytes(self, shape=None) -> int:
-        return self.height * self.width * 3
-
-    def release(self):
-        self.cap.release()
 
 
 # ---- libav through ctypes -----------------------------------------------------------------------------------
@@ -256,14 +226,17 @@ class LibavSource:
         self.opened = False
 
 
-def open_yuv_source(path: str):
+def open_yuv_source(path: str, cap=None):
     """A LibavSource positioned before the first picture, or None when the 4:2:0 route is not provably equivalent for
-    this file (then the caller uses cv2.VideoCapture, like the reference)."""
+    this file (then the caller uses cv2.VideoCapture, like the reference).  `cap`: an already opened cv2.VideoCapture of
+    the same file (for its rotation metadata); opened here when not given."""
     if os.environ.get("AVD_DECODE", "auto") == "cv2":
         return None
     try:
         import cv2
-        cap = cv2.VideoCapture(path)
+        own = cap is None
+        if own:
+            cap = cv2.VideoCapture(path)
         try:
             if not cap.isOpened():
                 return None
@@ -271,7 +244,8 @@ def open_yuv_source(path: str):
             if prop is not None and (cap.get(prop) or 0.0) != 0.0:
                 return None                                   # OpenCV would rotate the BGR frames
         finally:
-            cap.release()
+            if own:
+                cap.release()
         src = LibavSource(path)
         if not src.opened:
             src.release()

@@ -172,7 +172,7 @@ def analyze(path: str, meta: dict, engine=None) -> dict:
     duration = meta.get("duration") or (cap.get(cv2.CAP_PROP_FRAME_COUNT) / fps if fps > 0 else 0.0)
     step = sample_step(fps)
 
-    yuv = decode.open_yuv_source(path)
+    yuv = decode.open_yuv_source(path, cap)
     if yuv is not None:
         try:
             first = yuv.grab()                               # learns the pixel format; may refuse the stream
