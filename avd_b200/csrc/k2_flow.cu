@@ -118,10 +118,15 @@ __global__ void __launch_bounds__(256) pyr_kernel(ImgSrc src, float *__restrict_
 // pass of its 8 pixels out of shared memory.
 constexpr int PE_ROWS = 8, PE_HALO = 5;
 
-__global__ void __launch_bounds__(T) polyexp_kernel(const float *__restrict__ pyr, float *__restrict__ Rall, int k)
+#ifndef PE_MINB
+#define PE_MINB 4      /* 48 registers, 4 CTAs of 320 threads per SM: at 3 CTAs (62 registers) the kernel takes 272 instead of 207 us */
+#endif
+template <int K>
+__global__ void __launch_bounds__(T, PE_MINB) polyexp_kernel(const float *__restrict__ pyr, float *__restrict__ Rall)
 {
+    constexpr int k = K;
     extern __shared__ float pe_v[];                                    // [3][PE_ROWS][s + 2*PE_HALO]
-    const int s = lvl_size(k), vw = s + 2 * PE_HALO;
+    constexpr int s = lvl_size(k), vw = s + 2 * PE_HALO;       // level as a compile-time constant: offsets become immediates
     const float *I = pyr + (size_t)blockIdx.y * PYR_PX + lvl_off(k);
     float *R = Rall + (size_t)blockIdx.y * PYR_PX * 5 + (size_t)lvl_off(k) * 5;
     const int x = threadIdx.x, y0 = blockIdx.x * PE_ROWS;
@@ -159,8 +164,9 @@ __global__ void __launch_bounds__(T) polyexp_kernel(const float *__restrict__ py
     // 12-value window both pixels read from a row of moments comes in as six 64-bit shared-memory loads (33 32-bit loads
     // per pixel before: the kernel was throttled by the shared-memory instruction queue).  Per accumulator the operations
     // and their order are unchanged (each accumulator only ever sees one plane of moments).
-    const size_t plane = (size_t)s * s;
-    const int half = s >> 1, cp = x % half, r0 = (x / half) * (PE_ROWS / 2);
+    constexpr int plane = s * s;
+    constexpr int half = s >> 1;
+    const int cp = x % half, r0 = (x / half) * (PE_ROWS / 2);
 #pragma unroll 1
     for (int rr = 0; rr < PE_ROWS / 2; rr++) {
         const int r = r0 + rr;
@@ -598,7 +604,9 @@ int k2_flow(avd_ctx *ctx, const uint8_t *d_prev, const uint8_t *d_next, size_t p
         AVD_LAUNCH(ctx, "pyr", st, pyr_kernel<0><<<dim3(320 / PYR_CW, ni), 256, 0, st>>>(src, pyr));
         for (int k = 3; k >= 0; k--) {
             int s = lvl_size(k);
-            AVD_LAUNCH(ctx, "polyexp", st, polyexp_kernel<<<dim3(s / PE_ROWS, ni), (s + 31) / 32 * 32, 3 * PE_ROWS * (s + 2 * PE_HALO) * sizeof(float), st>>>(pyr, R, k));
+#define PE_LAUNCH(K) AVD_LAUNCH(ctx, "polyexp", st, polyexp_kernel<K><<<dim3(s / PE_ROWS, ni), (s + 31) / 32 * 32, 3 * PE_ROWS * (s + 2 * PE_HALO) * sizeof(float), st>>>(pyr, R))
+            if (k == 3) PE_LAUNCH(3); else if (k == 2) PE_LAUNCH(2); else if (k == 1) PE_LAUNCH(1); else PE_LAUNCH(0);
+#undef PE_LAUNCH
         }
         // Flow iterations (run_chain): um_kernel<K,.> + box_cs_kernel<K,.> per level, 3 iterations each.
         // AVD_K2_SPLIT=2: the pairs of the batch are split into two halves whose chains run on two streams, the second one
