@@ -61,8 +61,11 @@ __device__ __forceinline__ float blur_row(const uint8_t *__restrict__ row, int x
 // columns those outputs read, for all 320 source rows, go to shared memory once (the previous version recomputed them for
 // every output: 2-3x the work).  Phase B: column blur at the taps of each output and the resize arithmetic.
 constexpr int PYR_CW = 8;
+#ifndef PYR_MINB
+#define PYR_MINB 1
+#endif
 template <int K>
-__global__ void __launch_bounds__(256) pyr_kernel(ImgSrc src, float *__restrict__ pyr)
+__global__ void __launch_bounds__(256, PYR_MINB) pyr_kernel(ImgSrc src, float *__restrict__ pyr)
 {
     constexpr int S = lvl_size(K), ST = 1 << K, R = K == 0 ? 1 : (K == 1 ? 1 : (K == 2 ? 4 : 9)), N = K == 0 ? 1 : 2;
     constexpr int OFF = K == 2 ? 1 : (K == 3 ? 3 : 0), NC = PYR_CW * N;
@@ -338,8 +341,11 @@ __global__ void __launch_bounds__(256) um_kernel(const float *__restrict__ Rall,
 // per row; dense flow fields bit-identical (scripts/k2_fieldsha.py).
 // STATS: the last iteration of the finest level emits per-task sums of |flow| and |flow|^2 instead of the field.
 constexpr int BCS_THREADS = 160;
+#ifndef BCS_MINB
+#define BCS_MINB 1
+#endif
 template <int K, bool STATS>
-__global__ void __launch_bounds__(BCS_THREADS) box_cs_kernel(const float *__restrict__ Mall, float *__restrict__ flow, int seg_rows, int n_pairs,
+__global__ void __launch_bounds__(BCS_THREADS, BCS_MINB) box_cs_kernel(const float *__restrict__ Mall, float *__restrict__ flow, int seg_rows, int n_pairs,
                                                             double *__restrict__ task_stats, int p_base)
 {
     constexpr int S = lvl_size(K), STRIPS = bx_strips(S), plane = S * S;

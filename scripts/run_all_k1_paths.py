@@ -8,7 +8,7 @@ eng = Engine(0)
 for (H, W) in [(720, 1280), (1080, 1920), (1440, 2560), (2160, 3840), (648, 1344), (480, 640), (333, 777)]:
     fr = torch.randint(0, 256, (2, H, W, 3), dtype=torch.uint8, device="cuda")
     half = torch.full((1, H, W, 3), 100, dtype=torch.uint8, device="cuda"); half[:, :, 1::2, :] = 101
-    for mode in (0, 2, 1):
+    for mode in (0, 2, 3, 1):
         eng.set_k1_mode(mode)
         eng.frames_features(fr, want_area32=True)
     eng.set_k1_mode(0)
