@@ -374,3 +374,24 @@ def test_config3_clip_batch_vs_reference_golden(synth, eng):
         ref = gold[sd]
         assert parity.video_dict_vs_golden(o["video"], ref["video"]), (sd, o["video"], ref["video"])
         assert parity.fused_vs_golden(o["fusion"], ref["fused"]), (sd, o["fusion"], ref["fused"])
+
+
+def test_yuv_entry_point_argument_errors(torch, eng):
+    """The 4:2:0 entry points refuse what they cannot reproduce (odd sizes, short buffers, unknown formats) with an ordinary
+    exception, and the engine stays usable."""
+    from avd_b200._lib import AvdError
+    from avd_b200.engine import HostBatch
+    ok = np.zeros(64 * 96 * 3 // 2, np.uint8)
+    assert len(eng.analyze_host([ok, ok], fmt="i420", shape=(64, 96))) == 2
+    with pytest.raises(AvdError):
+        eng.analyze_host([np.zeros(65 * 96 * 3 // 2, np.uint8)], fmt="i420", shape=(65, 96))      # odd height
+    with pytest.raises(AvdError):
+        eng.analyze_host([ok[:-1]], fmt="i420", shape=(64, 96))                                    # short frame
+    with pytest.raises(AvdError):
+        HostBatch([ok], fmt="nv12", shape=(64, 96))
+    with pytest.raises(AvdError):
+        eng.analyze_host([ok], fmt="i420")                                                         # shape missing
+    with pytest.raises(AvdError):
+        eng.yuv420_to_bgr(torch.zeros((1, 33 * 34 * 3 // 2), dtype=torch.uint8, device="cuda"), 33, 34)
+    r = eng.analyze_host([ok, ok], fmt="j420", shape=(64, 96))
+    assert int(r[1]["ham_prev"]) == 0 and eng.check_guards() == 0
