@@ -67,7 +67,7 @@ struct avd_ctx {
     float *area_rows = nullptr; size_t area_rows_cap = 0;
     // K2 workspace (see k2_flow.cu)
     void *k2_ws = nullptr; size_t k2_ws_cap = 0; int k2_batch = 0;
-    cudaStream_t k2_side = nullptr; cudaEvent_t k2_ev[2] = {};   // second chain of a split batch (AVD_K2_SPLIT)
+    cudaStream_t k2_side[3] = {}; cudaEvent_t k2_ev[6] = {};     // further chains of a split batch (AVD_K2_SPLIT)
     // host streaming ring (avd_analyze_host)
     uint8_t *ring = nullptr; size_t ring_cap = 0;
     uint8_t *bgr_slot = nullptr; size_t bgr_slot_cap = 0;   // YUV input: the converted frames of the slot in flight

@@ -618,19 +618,25 @@ int k2_flow(avd_ctx *ctx, const uint8_t *d_prev, const uint8_t *d_next, size_t p
         // AVD_K2_SPLIT=2: the pairs of the batch are split into two halves whose chains run on two streams, the second one
         // launch behind the first, so that the memory-bound update_matrices of one half shares the SMs with the issue-bound
         // box_solve of the other.  A pair's arithmetic does not depend on which half it is in.
-        static const int split = getenv("AVD_K2_SPLIT") ? atoi(getenv("AVD_K2_SPLIT")) : 2;
+        static const int split_env = getenv("AVD_K2_SPLIT") ? atoi(getenv("AVD_K2_SPLIT")) : 2;
+        const int split = split_env < 1 ? 1 : (split_env > 4 ? 4 : split_env);
         ChainArgs A{R, M, flowA, flowB, tile_stats, mode, d_rec_first != nullptr};
-        if (split >= 2 && np >= 32) {      // measured: 119 pairs 1.52 -> 1.45 ms, 80: 1.08 -> 1.03, 40: 0.64 -> 0.63, 16: slower
-            if (!ctx->k2_side) {
-                AVD_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->k2_side, cudaStreamNonBlocking));
-                for (int i = 0; i < 2; i++) AVD_CUDA(ctx, cudaEventCreateWithFlags(&ctx->k2_ev[i], cudaEventDisableTiming));
+        if (split >= 2 && np >= 16 * split) {      // measured: 119 pairs 1.52 -> 1.45 ms, 80: 1.08 -> 1.03, 40: 0.64 -> 0.63, 16: slower
+            if (!ctx->k2_side[0]) {
+                for (int i = 0; i < 3; i++) AVD_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->k2_side[i], cudaStreamNonBlocking));
+                for (int i = 0; i < 6; i++) AVD_CUDA(ctx, cudaEventCreateWithFlags(&ctx->k2_ev[i], cudaEventDisableTiming));
             }
-            const int h = (np + 1) / 2;
-            if ((rc = run_chain(ctx, st, A, 0, h, ctx->k2_ev[0]))) return rc;          // k2_ev[0]: recorded behind the first launch
-            AVD_CUDA(ctx, cudaStreamWaitEvent(ctx->k2_side, ctx->k2_ev[0], 0));
-            if ((rc = run_chain(ctx, ctx->k2_side, A, h, np - h, nullptr))) return rc;
-            AVD_CUDA(ctx, cudaEventRecord(ctx->k2_ev[1], ctx->k2_side));
-            AVD_CUDA(ctx, cudaStreamWaitEvent(st, ctx->k2_ev[1], 0));
+            // chain c runs pairs [c*np/split, (c+1)*np/split) on its own stream, one launch behind chain c-1
+            for (int c = 0; c < split; c++) {
+                const int q0 = (int)((long long)np * c / split), q1 = (int)((long long)np * (c + 1) / split);
+                cudaStream_t cs = c == 0 ? st : ctx->k2_side[c - 1];
+                if (c > 0) AVD_CUDA(ctx, cudaStreamWaitEvent(cs, ctx->k2_ev[c - 1], 0));
+                if ((rc = run_chain(ctx, cs, A, q0, q1 - q0, c + 1 < split ? ctx->k2_ev[c] : nullptr))) return rc;
+                if (c > 0) {
+                    AVD_CUDA(ctx, cudaEventRecord(ctx->k2_ev[3 + c - 1], cs));
+                    AVD_CUDA(ctx, cudaStreamWaitEvent(st, ctx->k2_ev[3 + c - 1], 0));
+                }
+            }
         } else if ((rc = run_chain(ctx, st, A, 0, np, nullptr))) return rc;
         float *prev = flowB;                       // levels 3..0 write flowA, flowB, flowA, flowB: the finest flow ends in flowB
         if (d_rec_first) {
