@@ -413,3 +413,100 @@ def test_service_analyze_path_neutral_results_without_decoders(tmp_path):
     assert "error" in out["audio"]["flags_audio"] and out["audio"]["timeline"] == [0.5, 0.5, 0.5]
     assert set(out) == {"hints", "video", "audio", "result", "timeline_binned", "peaks"}
     assert out["result"]["label"] in ("real", "uncertain", "ai") and len(out["timeline_binned"]) == 3
+
+
+class _FakeEngine:
+    """Stands in for Engine in host-logic tests: `analyze_host` 'analyses' a frame by reading its first byte; a record's
+    ham_prev is the previous frame's first byte (or -1), so chains, halos and ordering are observable without a GPU."""
+
+    def __init__(self):
+        import threading
+        self._lock = threading.RLock()
+        self.calls, self.live = [], 0
+
+    def staging(self, nbytes):
+        import contextlib
+
+        @contextlib.contextmanager
+        def cm():
+            self.live += 1
+            try:
+                yield np.zeros(int(nbytes), np.uint8)
+            finally:
+                self.live -= 1
+        return cm()
+
+    def analyze_host(self, frames, keep_on_device=False, fmt="bgr", shape=None):
+        from avd_b200._lib import REC_DTYPE
+        n = len(frames)
+        first = [int(np.asarray(frames[i]).reshape(-1)[0]) for i in range(n)]
+        self.calls.append((fmt, n, first))
+        recs = np.zeros(n, REC_DTYPE)
+        for i in range(n):
+            recs["lap_sum"][i] = first[i]
+            recs["ham_prev"][i] = first[i - 1] if i else -1
+            recs["flags"][i] = 3 if i else 0
+        return recs
+
+
+def test_decode_run_pipeline_halo_order_and_staging():
+    """video._RunPipeline (decode of run k+1 overlapped with the device work of run k): every sampled frame is analysed
+    exactly once and in order, every run after the first is seeded with the previous run's last frame in its halo slot and
+    that record is dropped, and the staging buffers are returned only after the worker is done."""
+    from avd_b200 import video
+    eng = _FakeEngine()
+    nb, n = 6 * 4 * 3, 2 * video.DECODE_RUN + 7                 # tiny 6x4 BGR frames, two full runs and a partial one
+    import contextlib
+    with contextlib.ExitStack() as stack:
+        stages = [stack.enter_context(eng.staging((video.DECODE_RUN + 1) * nb)) for _ in range(2)]
+        pipe = video._RunPipeline(eng, stages, nb, "bgr", (6, 4))
+        try:
+            for i in range(n):
+                pipe.slot()[:] = (i + 1) % 251
+                pipe.pushed()
+            recs = pipe.finish()
+        finally:
+            pipe.close()
+        assert eng.live == 2
+    assert eng.live == 0
+    assert [int(x) for x in recs["lap_sum"]] == [(i + 1) % 251 for i in range(n)]
+    assert int(recs["ham_prev"][0]) == -1
+    assert [int(x) for x in recs["ham_prev"][1:]] == [(i + 1) % 251 for i in range(n - 1)]      # the chain crosses the runs
+    assert [c[1] for c in eng.calls] == [video.DECODE_RUN, video.DECODE_RUN + 1, 8]               # runs 2 and 3 carry a halo frame
+    assert eng.calls[1][2][0] == video.DECODE_RUN % 251 and eng.calls[2][2][0] == (2 * video.DECODE_RUN) % 251
+
+
+def test_engine_pool_leases_and_bounds(monkeypatch):
+    """engine.EnginePool: at most `size` contexts, a lease blocks until one is free, an explicit engine bypasses the pool."""
+    import threading
+    import time
+    from avd_b200 import engine as E
+    made = []
+
+    class Fake:
+        def __init__(self, device):
+            made.append(self)
+
+        def close(self):
+            pass
+
+    monkeypatch.setattr(E, "Engine", Fake)
+    pool = E.EnginePool(0, size=2)
+    got, gate = [], threading.Event()
+
+    def work():
+        with pool.lease() as e:
+            got.append(e)
+            gate.wait(2.0)
+
+    ts = [threading.Thread(target=work) for _ in range(3)]
+    [t.start() for t in ts]
+    time.sleep(0.2)
+    assert len(made) == 2 and len(got) == 2                      # the third caller waits for a context
+    gate.set()
+    [t.join() for t in ts]
+    assert len(made) == 2 and len(got) == 3 and got[2] in made
+    sentinel = object()
+    with E.lease(sentinel) as e:
+        assert e is sentinel
+    pool.close()
