@@ -5,7 +5,7 @@
 // Same decomposition as the fused kernels: CTA = (frame, band b), band b = the source rows owned by INTER_AREA
 // destination row b plus one halo row above and below (REFLECT_101 rows at the frame edges are loaded as the halo).
 // The band's gray rows live in shared memory (u8); everything else reads them from there:
-//   gray        video.py:5,43,51   one thread per 4 pixels: three 32-bit loads when the row is 4-byte aligned, bytes otherwise
+//   gray        video.py:5,43,51   a warp per row, a lane per 4 pixels: aligned 32-bit loads + funnel shift by the row's misalignment
 //   Laplacian   video.py:52        exact integer sums, one 64-bit atomic pair per CTA
 //   INTER_AREA  video.py:6         the library's float32 arithmetic in the library's ORDER: horizontal pass,
 //                                  one thread per (row, cell column), sequential adds; vertical pass, one thread per cell
@@ -26,7 +26,6 @@ struct KRParams {
     const ShapeTables *tab;
     avd_sample_rec *rec;
     uint8_t *thumbs, *area32;
-    int aligned4;                      // every row starts on a 4-byte boundary
 };
 
 __device__ __forceinline__ uint32_t gray_of(uint32_t b, uint32_t g, uint32_t r) { return (3735u * b + 19235u * g + 9798u * r + 16384u) >> 15; }
@@ -57,12 +56,20 @@ __global__ void __launch_bounds__(KR_THREADS) k1_rows_kernel(KRParams P)
         const int r = r101(own0 - 1 + q, H);
         const uint8_t *rowp = frame + (size_t)r * P.pitch;
         uint32_t *grow = (uint32_t *)(G + (size_t)q * Wp);
+        // a row of a dense ragged-width frame starts at any byte: aligned 32-bit loads + a funnel shift by the row's misalignment
+        // (the same for every group of the row, since a group is 12 bytes)
+        const uint32_t mis = (uint32_t)((uintptr_t)rowp & 3u), sh = 8u * mis;
         for (int g4 = lane; g4 < groups; g4 += 32) {
             const int x = 4 * g4;
             const uint8_t *src = rowp + 3 * x;
             uint32_t out;
-            if (P.aligned4 && x + 4 <= W) {
-                const uint32_t w0 = ((const uint32_t *)src)[0], w1 = ((const uint32_t *)src)[1], w2 = ((const uint32_t *)src)[2];
+            if (x + 4 <= W) {
+                const uint32_t *al = (const uint32_t *)(src - mis);
+                uint32_t w0 = al[0], w1 = al[1], w2 = al[2];
+                if (mis) {                                       // warp-uniform
+                    const uint32_t w3 = al[3];                   // holds bytes of this group: never past the row's last pixel
+                    w0 = __funnelshift_r(w0, w1, sh); w1 = __funnelshift_r(w1, w2, sh); w2 = __funnelshift_r(w2, w3, sh);
+                }
                 out = gray_of(w0 & 255u, (w0 >> 8) & 255u, (w0 >> 16) & 255u)
                     | gray_of(w0 >> 24, w1 & 255u, (w1 >> 8) & 255u) << 8
                     | gray_of((w1 >> 16) & 255u, w1 >> 24, w2 & 255u) << 16
@@ -220,7 +227,6 @@ int k1_rows(avd_ctx *ctx, const uint8_t *d_bgr, int n, int H, int W, size_t pitc
     KRParams P{};
     P.bgr = d_bgr; P.pitch = pitch; P.fstride = fstride; P.H = H; P.W = W; P.Wp = (W + 3) & ~3;
     P.tab = tab; P.rec = d_rec; P.thumbs = d_thumbs; P.area32 = d_area32;
-    P.aligned4 = ((uintptr_t)d_bgr % 4 == 0 && pitch % 4 == 0 && fstride % 4 == 0) ? 1 : 0;
     const size_t smem = kr_smem_bytes(H, W, htab);
     static size_t smem_set[64] = {};
     size_t &set = smem_set[ctx->device & 63];
