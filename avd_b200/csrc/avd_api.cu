@@ -344,7 +344,7 @@ int avd_shape_plan(int H, int W, avd_shape_plan_t *out)
     // which per-frame kernel a dense, 16-byte aligned buffer of this shape gets (0 streaming, 2 banded, 3 any-width fused, 1 generic)
     const size_t pitch = (size_t)W * 3;
     out->k1_path = k1_fused_supported(H, W, pitch, pitch * H, nullptr, &t) ? 0 :
-                   (k1_banded_supported(H, W, pitch, pitch * H, nullptr) ? 2 : (k1_rows_supported(H, W, &t) ? 3 : 1));
+                   (k1_rows_supported(H, W, &t) ? 3 : (k1_banded_supported(H, W, pitch, pitch * H, nullptr) ? 2 : 1));
     return AVD_OK;
 }
 
@@ -383,18 +383,25 @@ int avd_frames_features(avd_ctx *ctx, const uint8_t *d_bgr, int n, int H, int W,
     }
     K1FixArgs fix{d_bgr, row_pitch, frame_stride, tab, nullptr};
     // the streaming kernel writes the thumbnail rows with 128-bit stores
-    const bool streaming = ctx->k1_mode == 0 && ((uintptr_t)d_thumbs % 16) == 0 && k1_fused_supported(H, W, row_pitch, frame_stride, d_bgr, htab);
-    if (streaming) {
+    // 0 streaming (TMA) kernel, 2 banded kernel, 3 any-width kernel, 1 generic multi-kernel path
+    int path = 1;
+    if (ctx->k1_mode == 0 && ((uintptr_t)d_thumbs % 16) == 0 && k1_fused_supported(H, W, row_pitch, frame_stride, d_bgr, htab)) path = 0;
+    else if (ctx->k1_mode == 2 && k1_banded_supported(H, W, row_pitch, frame_stride, d_bgr)) path = 2;
+    else if (ctx->k1_mode != 1 && k1_rows_supported(H, W, htab) && (unsigned long long)row_pitch * (unsigned long long)H < (1ull << 32)) path = 3;
+    else if (ctx->k1_mode == 0 && k1_banded_supported(H, W, row_pitch, frame_stride, d_bgr)) path = 2;
+    // the streaming and the any-width kernel list the INTER_AREA cells they cannot certify; area_fix_kernel recomputes them
+    const bool lists = path == 0 || path == 3;
+    if (lists) {
         if ((rc = avd_ensure(ctx, (void **)&ctx->fixlist, &ctx->fixlist_cap, ((size_t)n * 1024 + 1) * sizeof(uint32_t)))) return rc;
         fix.list = ctx->fixlist;
     }
-    if ((rc = k1_rec_init(ctx, d_rec, n, streaming ? ctx->fixlist : nullptr, st))) return rc;
-    if (streaming)
+    if ((rc = k1_rec_init(ctx, d_rec, n, lists ? ctx->fixlist : nullptr, st))) return rc;
+    if (path == 0)
         rc = k1_fused(ctx, d_bgr, n, H, W, row_pitch, frame_stride, tab, htab, d_rec, d_thumbs, d_area32, ctx->fixlist, st);
-    else if ((ctx->k1_mode == 0 || ctx->k1_mode == 2) && k1_banded_supported(H, W, row_pitch, frame_stride, d_bgr))
+    else if (path == 2)
         rc = k1_banded(ctx, d_bgr, n, H, W, row_pitch, frame_stride, tab, htab, d_rec, d_thumbs, d_area32, st);
-    else if (ctx->k1_mode != 1 && k1_rows_supported(H, W, htab))
-        rc = k1_rows(ctx, d_bgr, n, H, W, row_pitch, frame_stride, tab, htab, d_rec, d_thumbs, d_area32, st);
+    else if (path == 3)
+        rc = k1_rows(ctx, d_bgr, n, H, W, row_pitch, frame_stride, tab, htab, d_rec, d_thumbs, d_area32, ctx->fixlist, st);
     else
         rc = k1_generic(ctx, d_bgr, n, H, W, row_pitch, frame_stride, tab, htab, d_rec, d_thumbs, d_area32, st);
     if (rc) return rc;

@@ -146,7 +146,7 @@ int k0_yuv420_to_bgr(avd_ctx *ctx, const uint8_t *d_yuv, size_t yuv_stride, int 
 bool k1_rows_supported(int H, int W, const ShapeTables *htab);
 int k1_rows(avd_ctx *ctx, const uint8_t *d_bgr, int n, int H, int W, size_t pitch, size_t fstride,
             const ShapeTables *tab, const ShapeTables *htab, avd_sample_rec *d_rec, uint8_t *d_thumbs,
-            uint8_t *d_area32, cudaStream_t st);
+            uint8_t *d_area32, uint32_t *d_fixlist, cudaStream_t st);
 // k2_flow.cu
 int k2_reserve(avd_ctx *ctx, int n_pairs);   // size the workspace for runs of up to n_pairs pairs now
 int k2_flow(avd_ctx *ctx, const uint8_t *d_prev, const uint8_t *d_next, size_t prev_stride, size_t next_stride,

@@ -156,6 +156,31 @@ def test_area_rounding_boundaries(torch, eng, oracle):
     assert outs[0][0] == outs[1][0] and np.array_equal(outs[0][1], outs[1][1])
 
 
+def test_any_width_kernel_area_rounding_boundaries(torch, eng, oracle):
+    """k1_rows.cu computes INTER_AREA cells as exact integers and lists the cells whose mean is within the float32 summation
+    error of a rounding boundary for area_fix_kernel (the library's order): frames built so that many / all cells sit on or
+    next to k + 0.5, on ragged, fractional-scale and integer-scale shapes, against the generic path and the oracle."""
+    rng = np.random.default_rng(12)
+    for (H, W) in [(480, 854), (768, 1366), (480, 640), (333, 777), (600, 1920)]:
+        frames = []
+        g = np.full((H, W), 100, np.uint8); g[:, 1::2] = 101; frames.append(g)               # column stripes: means near 100.5
+        g = np.full((H, W), 7, np.uint8); g[::2, :] = 8; frames.append(g)                     # row stripes, fractional rows
+        g = (100 + (rng.random((H, W)) < 0.5)).astype(np.uint8); frames.append(g)             # means scattered around 100.5
+        g = np.full((H, W), 255, np.uint8); g[:, ::2] = 254; frames.append(g)                 # 254.5: saturation side
+        g = rng.integers(0, 256, (H, W), dtype=np.uint8); frames.append(g)
+        bgr = np.stack([np.repeat(x[:, :, None], 3, axis=2) for x in frames])                 # B=G=R=v -> gray = v
+        d = torch.from_numpy(bgr).cuda()
+        outs = {}
+        for mode in (3, 1):
+            eng.set_k1_mode(mode)
+            rec, th, ar = eng.frames_features(d, want_area32=True)
+            outs[mode] = (rec.cpu().numpy().tobytes(), ar.cpu().numpy())
+        eng.set_k1_mode(0)
+        for i, x in enumerate(frames):
+            assert np.array_equal(outs[3][1][i], oracle.area32(x)), (H, W, i)
+        assert outs[3][0] == outs[1][0] and np.array_equal(outs[3][1], outs[1][1]), (H, W)
+
+
 def test_streaming_kernel_padded_pitch(synth, torch, eng):
     """Row pitch > 3W (16-byte aligned) and a frame stride > H*pitch through the streaming kernel."""
     H, W = 720, 1280

@@ -276,12 +276,14 @@ def test_shape_plan_row_roles(shape):
 
 
 def test_shape_plan_kernel_choice():
-    """Which per-frame kernel a dense aligned buffer gets: 0 streaming fused, 2 banded fused, 3 any-width fused (a band of
-    gray rows in shared memory), 1 generic (bands too large for shared memory)."""
+    """Which per-frame kernel a dense aligned buffer gets: 0 streaming (TMA) kernel, 3 any-width kernel (a band of gray rows in
+    shared memory; round 2: faster than the banded kernel on every shape both take), 2 banded kernel (W % 16 == 0 bands too
+    large for the any-width kernel's shared memory), 1 generic (ragged widths with such bands)."""
     want = {(1080, 1920): 0, (720, 1280): 0, (1440, 2560): 0, (2160, 3840): 0, (648, 1344): 0, (960, 1280): 0,
-            (480, 640): 2, (640, 640): 2, (360, 640): 2, (1080, 1936): 2,   # W % 16 == 0 only
-            (480, 854): 3, (333, 777): 3, (768, 1366): 3, (32, 32): 2, (2160, 3838): 1, (33, 35): 3,
-            (600, 1920): 2}                                                   # H < 640: a tap row would have two roles
+            (480, 640): 3, (640, 640): 3, (360, 640): 3, (1080, 1936): 3,   # W % 16 == 0 but below / off the streaming kernel's grid
+            (480, 854): 3, (333, 777): 3, (768, 1366): 3, (32, 32): 3, (33, 35): 3,
+            (600, 1920): 3,                                                   # H < 640: a tap row would have two roles
+            (2160, 3856): 2, (2160, 3838): 1}
     for (H, W), k in want.items():
         assert _plan(H, W).k1_path == k, (H, W)
     assert _plan(960, 1280).area_int == 1 and _plan(1080, 1920).area_int == 0 and _plan(640, 640).thumb_2x2 == 1
