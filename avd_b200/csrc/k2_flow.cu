@@ -342,7 +342,7 @@ __global__ void __launch_bounds__(256) um_kernel(const float *__restrict__ Rall,
 // STATS: the last iteration of the finest level emits per-task sums of |flow| and |flow|^2 instead of the field.
 constexpr int BCS_THREADS = 160;
 #ifndef BCS_MINB
-#define BCS_MINB 1
+#define BCS_MINB 6      /* 64 registers, 6 CTAs of 160 threads per SM; unbounded the compiler takes 94 (4 CTAs): 1.475 -> 1.398 ms per 119 pairs */
 #endif
 template <int K, bool STATS>
 __global__ void __launch_bounds__(BCS_THREADS, BCS_MINB) box_cs_kernel(const float *__restrict__ Mall, float *__restrict__ flow, int seg_rows, int n_pairs,
