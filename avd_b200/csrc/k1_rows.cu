@@ -345,18 +345,18 @@ __global__ void __launch_bounds__(KR_THREADS, KR_MINB) k1_rows_kernel(KRParams P
         atomicAdd((unsigned long long *)&P.rec[f].lap_sum, (unsigned long long)a);
         atomicAdd((unsigned long long *)&P.rec[f].lap_sumsq, (unsigned long long)c2);
     }
-    {
+    if (tid < 32) {
         // cell column dx covers [dx W / 32, (dx + 1) W / 32): head pixel xs0 - 1 (weight oh), pixels xs0 .. xs1 - 1 (32), the
-        // last one of them with weight ot.  Eight threads per cell (exact integers: any order).
-        const int dx = tid >> 3, part = tid & 7;
+        // last one of them with weight ot (exact integers: any order)
+        const int dx = tid;
         const int xs0 = (dx * W + 31) >> 5, xs1 = ((dx + 1) * W + 31) >> 5;
         const int oh = 32 * xs0 - dx * W, ot = (dx + 1) * W - 32 * (xs1 - 1);
-        unsigned long long acc = 0;
-        for (int x = xs0 + part; x < xs1; x += 8) acc += (unsigned)V[x];
-        acc *= 32ull;
-        if (part == 0) acc += (unsigned long long)oh * (unsigned)V[max(xs0 - 1, 0)];
-        if (part == 1) acc -= (unsigned long long)(32 - ot) * (unsigned)V[xs1 - 1];
-        acc += __shfl_xor_sync(0xffffffffu, acc, 1); acc += __shfl_xor_sync(0xffffffffu, acc, 2); acc += __shfl_xor_sync(0xffffffffu, acc, 4);
+        uint32_t a0 = 0, a1 = 0;                                     // V <= 32 * 255 * (rows + 1), <= 130 columns: < 2^32
+        int x = xs0;
+        for (; x + 2 <= xs1; x += 2) { a0 += (unsigned)V[x]; a1 += (unsigned)V[x + 1]; }
+        if (x < xs1) a0 += (unsigned)V[x];
+        const unsigned long long acc = 32ull * ((unsigned long long)a0 + a1) + (unsigned long long)oh * (unsigned)V[max(xs0 - 1, 0)]
+                                       - (unsigned long long)(32 - ot) * (unsigned)V[xs1 - 1];
         const uint32_t M = (uint32_t)acc;                            // = mean * W * H <= 255 W H < 2^32
         uint32_t out;
         bool close = false;
@@ -368,11 +368,11 @@ __global__ void __launch_bounds__(KR_THREADS, KR_MINB) k1_rows_kernel(KRParams P
             const uint32_t k = M / Dn, r = M - k * Dn;
             const long long d2 = 2ll * r - (long long)Dn;
             const uint32_t bound = (uint32_t)(((unsigned long long)M * (uint32_t)(17 * ((W >> 5) + 2 + n + 1 + 4))) >> 27) + 2u;
-            close = part == 0 && (unsigned long long)(d2 < 0 ? -d2 : d2) <= bound;
+            close = (unsigned long long)(d2 < 0 ? -d2 : d2) <= bound;
             out = k + (d2 >= 0 ? 1u : 0u);
         }
-        if (part == 0) P.area32[(size_t)f * 1024 + b * 32 + dx] = (uint8_t)out;
-        // uncertified cells go to the fix list (per warp: four cells)
+        P.area32[(size_t)f * 1024 + b * 32 + dx] = (uint8_t)out;
+        // uncertified cells go to the fix list
         const uint32_t mask = __ballot_sync(0xffffffffu, close);
         if (mask) {
             uint32_t base = 0;

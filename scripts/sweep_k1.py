@@ -37,7 +37,7 @@ def _cpu_worker(args):
 def main():
     import multiprocessing as mp
     cores = len(os.sched_getaffinity(0))
-    shapes = [(480, 854), (480, 640), (768, 1366), (720, 1280), (1080, 1920), (1440, 2560), (2160, 3840)]
+    shapes = [(360, 640), (480, 854), (480, 640), (540, 960), (768, 1366), (720, 1280), (1080, 1920), (1440, 2560), (2160, 3840)]
     cpu = {}
     with mp.get_context("fork").Pool(cores) as pool:       # before CUDA is touched
         for (H, W) in shapes:
