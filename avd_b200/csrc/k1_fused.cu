@@ -34,6 +34,7 @@
 // round(mean).  The few cells (~0.2 %) that are closer are listed and recomputed in the library's exact float32
 // order by area_fix_kernel (k1_generic.cu), off this kernel's critical path.
 #include "avd_internal.h"
+#include <stdlib.h>
 
 namespace {
 
@@ -66,6 +67,7 @@ struct K1Params {
     uint8_t *thumbs, *area32;
     uint32_t *fixlist;                // [0] = count (zeroed by k1_rec_init), then frame * 1024 + cell
     int frame0;
+    int nframes;                      // frames of this launch (PAIR form: the last CTA row may hold a single frame)
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -161,9 +163,9 @@ struct Band {
     uint32_t stage;                       // shared address of stage 0
     uint32_t slot;                        // shared address of this thread's private gray slot
     uint32_t sp0, rb1, rb2;               // this thread's strip in stage 0; one and two rows in bytes
-    int row_bytes, nseq;
+    int row_bytes, nseq;                  // bytes of one frame row (one bulk copy)
     int H, own0;
-    const uint8_t *frame;
+    const uint8_t *frame, *frame2;        // PAIR form: the second frame's rows land right behind the first one's in a stage
     size_t pitch;
     uint64_t pol_stream, pol_keep;
     GrayK K;
@@ -277,10 +279,12 @@ __device__ __forceinline__ void issue_row(const Band &B, int q, uint32_t stage_o
     int r = B.own0 - 1 + q;
     r = r < 0 ? 1 : (r >= B.H ? B.H - 2 : r);
     const uint32_t bar = B.sbase + OFF_FULL + bar_off;
-    mbar_expect_tx(bar, (uint32_t)B.row_bytes);
+    mbar_expect_tx(bar, (uint32_t)B.row_bytes * (B.frame2 ? 2u : 1u));
     // the two first and two last rows of a band are also read by the neighbouring bands: do not mark them evict-first
     const bool shared_row = q < 2 || q >= B.nseq - 2;
     tma_load_1d(B.stage + stage_off, B.frame + (size_t)r * B.pitch, (uint32_t)B.row_bytes, bar, shared_row ? B.pol_keep : B.pol_stream);
+    if (B.frame2)
+        tma_load_1d(B.stage + stage_off + (uint32_t)B.row_bytes, B.frame2 + (size_t)r * B.pitch, (uint32_t)B.row_bytes, bar, shared_row ? B.pol_keep : B.pol_stream);
 }
 
 // Stage s holds sequence row q: convert this thread's strip to gray (row set R); on tap rows of the thumbnail also
@@ -361,7 +365,7 @@ __device__ __forceinline__ uint32_t load_row(const Band &B, int q, uint32_t goff
 template <int POS>
 __device__ __forceinline__ void release_finish(const Band &B, int q, uint32_t goff, uint32_t gbar, uint32_t ticket)
 {
-    if (ticket == 1u && q + NRS < B.nseq) issue_row(B, q + NRS, goff + POS * B.row_bytes, gbar + 8 * POS);
+    if (ticket == 1u && q + NRS < B.nseq) issue_row(B, q + NRS, goff + POS * B.rb1, gbar + 8 * POS);
 }
 
 __device__ __forceinline__ uint8_t sat_rne(float v)
@@ -379,28 +383,36 @@ __device__ __forceinline__ uint32_t masked_sum(const uint32_t *P, const uint32_t
     return s;
 }
 
-template <int MAXT, int MINB, int JT, int TM>
+// PAIR: a CTA takes band b of TWO consecutive frames side by side (thread tid < W/16: frame 2y, the others: frame 2y+1).  At
+// W = 1280 a frame has 80 strips = 2.5 warps; alone, a sixth of the CTA's lanes idles and the band's fixed cost (barrier set-up,
+// first fill of the ring, epilogue) is spread over few bytes; two frames are 160 strips = 5 full warps.
+template <int MAXT, int MINB, int JT, int TM, bool PAIR = false>
 __global__ void __launch_bounds__(MAXT, MINB) k1_fused_kernel(K1Params P)
 {
     extern __shared__ __align__(128) uint8_t smem[];
     const int tid = threadIdx.x, lane = tid & 31;
     const int nthr = blockDim.x, nw = nthr >> 5;
-    const int b = blockIdx.x, f = blockIdx.y;
+    const int b = blockIdx.x;
     const ShapeTables *__restrict__ tab = P.tab;
     const int H = P.H, W = P.W;
+    const int S = W >> 4;                                     // strips of a frame
+    const int half = PAIR && tid >= S ? 1 : 0, lt = tid - half * S;       // which of the CTA's frames, strip inside it
+    const int f = PAIR ? 2 * (int)blockIdx.y + half : (int)blockIdx.y;
+    const bool have2 = PAIR && 2 * (int)blockIdx.y + 1 < P.nframes;
+    const uint32_t stride = (PAIR ? 2u : 1u) * (uint32_t)P.row_bytes;      // bytes of a stage
     const int own0 = tab->row_owner_begin[b], own1 = tab->row_owner_begin[b + 1];
     const int n = own1 - own0, nseq = n + 2;
     uint32_t sbase;                         // opaque, or the compiler recomputes the shared window address at every use
     asm volatile("mov.u32 %0, %1;" : "=r"(sbase) : "r"(smem_u32(smem)));
-    const uint8_t *frame = P.bgr + (size_t)f * P.fstride;
+    const uint8_t *frame0 = P.bgr + (size_t)(PAIR ? 2 * (int)blockIdx.y : (int)blockIdx.y) * P.fstride;
 
     Band B;
-    B.sbase = sbase; B.stage = sbase + HDR; B.slot = sbase + HDR + NRS * P.row_bytes + 64 + SLOT * tid;
+    B.sbase = sbase; B.stage = sbase + HDR; B.slot = sbase + HDR + NRS * stride + 64 + SLOT * tid;
     B.row_bytes = P.row_bytes; B.nseq = nseq;
-    B.sp0 = sbase + HDR + 48 * tid; B.rb1 = (uint32_t)P.row_bytes; B.rb2 = 2u * (uint32_t)P.row_bytes;
+    B.sp0 = sbase + HDR + 48 * tid; B.rb1 = stride; B.rb2 = 2u * stride;
     B.K.load();
     B.todd = tab->lx[0].i0 & 1;
-    B.H = H; B.own0 = own0; B.frame = frame; B.pitch = P.pitch;
+    B.H = H; B.own0 = own0; B.frame = frame0; B.frame2 = have2 ? frame0 + P.fstride : nullptr; B.pitch = P.pitch;
     asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(B.pol_stream));
     asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(B.pol_keep));
 
@@ -411,9 +423,9 @@ __global__ void __launch_bounds__(MAXT, MINB) k1_fused_kernel(K1Params P)
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        for (int q = 0; q < NRS; q++) issue_row(B, q, q * P.row_bytes, 8 * q);
+        for (int q = 0; q < NRS; q++) issue_row(B, q, q * stride, 8 * q);
     }
-    if (tid < 32) ((int *)(smem + OFF_CELL))[tid] = 0;
+    if (tid < (PAIR ? 64 : 32)) ((int *)(smem + OFF_CELL))[tid] = 0;
     if (tid == 32) ((uint32_t *)(smem + OFF_MISC))[1] = 0;          // warps that finished the band
     // thumbnail role of the band's rows: the top tap row must be owned by this band, the bottom tap is the row below it
     for (int q = tid; q < nseq; q += nthr) {
@@ -425,30 +437,31 @@ __global__ void __launch_bounds__(MAXT, MINB) k1_fused_kernel(K1Params P)
     // this thread's thumbnail columns
     Thumb<JT> T;
     {
-        const int tx0 = tab->strip_tx0[tid];
-        T.ntx = 16 * tid < W ? tab->strip_ntx[tid] : 0;
+        const int tx0 = tab->strip_tx0[lt];
+        T.ntx = (16 * lt < W && (half == 0 || have2)) ? tab->strip_ntx[lt] : 0;
         T.dst = P.thumbs + (size_t)f * AVD_T * AVD_T + tx0;
-        T.th = B.slot - SLOT * tid + SLOT * nthr + 64 + tx0 - (uint32_t)(tab->thumb_row_begin[b] * AVD_T);   // row index comes as an absolute thumbnail row
+        T.th = B.slot - SLOT * tid + SLOT * nthr + 64 + tx0 - (uint32_t)(tab->thumb_row_begin[b] * AVD_T)     // row index comes as an absolute thumbnail row
+               + (uint32_t)(half * MAX_TROWS * AVD_T);
 #pragma unroll
         for (int k = 0; k < JT; k++) {
             const LinTap t = tab->lx[min(tx0 + k, AVD_T - 1)];
             const bool ok = k < T.ntx;
-            const int rel = t.i0 - 16 * tid;                            // left tap, relative to the strip
+            const int rel = t.i0 - 16 * lt;                             // left tap, relative to the strip
             T.addr[k] = B.slot + (ok ? (uint32_t)((TM != 0) ? 2 * (rel >> 1) : rel) : 0u);   // pair form: 16-bit lane rel/2 (even) or (rel-1)/2 (odd)
             T.a0[k] = (uint32_t)t.a0; T.a1[k] = (uint32_t)t.a1; T.u0[k] = 0;
         }
     }
     __syncthreads();
 
-    const bool active = 16 * tid < W, first = tid == 0, last = 16 * tid + 16 == W;
+    const bool active = 16 * lt < W && (half == 0 || have2), first = lt == 0, last = 16 * lt + 16 == W;
     RowSet R0, R1, R2;
     Acc A;
     A.ll = A.hl = A.hh = 0; A.aLR = A.aE0 = A.aO3 = 0; A.cs[0] = A.cs[1] = A.cs[2] = A.cs[3] = 0;
 
     // INTER_AREA: this strip's pair lanes split between cell cA (pairs < kA) and cell cA+1
     const int sx = W >> 5;
-    const int cA = (16 * tid) / sx;
-    const int kA = min(8, ((cA + 1) * sx - 16 * tid) >> 1);
+    const int cA = (16 * lt) / sx;
+    const int kA = min(8, ((cA + 1) * sx - 16 * lt) >> 1);
     uint32_t mA[4];
 #pragma unroll
     for (int g = 0; g < 4; g++) mA[g] = (2 * g < kA ? 1u : 0u) | (2 * g + 1 < kA ? 0x100u : 0u);
@@ -457,7 +470,7 @@ __global__ void __launch_bounds__(MAXT, MINB) k1_fused_kernel(K1Params P)
     const int wt = (b + 1) * H - 32 * (own1 - 1);         // weight of the last owned row, 1/32 units (32 = full)
 
     // stage group state: byte offset of the group's first stage / first barrier (toggled, never multiplied), phase parity
-    const uint32_t g3 = NGRP > 1 ? 3u * (uint32_t)P.row_bytes : 0u, gb3 = NGRP > 1 ? 24u : 0u;
+    const uint32_t g3 = NGRP > 1 ? 3u * stride : 0u, gb3 = NGRP > 1 ? 24u : 0u;
     const uint32_t fbar = sbase + OFF_FULL;
     uint32_t par = 0, goff = 0, gbar = 0;
     uint32_t ok = mbar_try(fbar, 0u);
@@ -534,17 +547,37 @@ __global__ void __launch_bounds__(MAXT, MINB) k1_fused_kernel(K1Params P)
     long long sumL2 = (long long)((unsigned long long)A.ll + 512ull * A.hl + 65536ull * A.hh) - 2040ll * sumL - 1040400ll * (16ll * n);
     int *cellM = (int *)(smem + OFF_CELL);
     if (active) {
-        atomicAdd(&cellM[cA], mcA);
-        if (kA < 8) atomicAdd(&cellM[cA + 1], mcB);
+        atomicAdd(&cellM[32 * half + cA], mcA);
+        if (kA < 8) atomicAdd(&cellM[32 * half + cA + 1], mcB);
     } else {
         sumL = 0; sumL2 = 0;
     }
-    for (int o = 16; o; o >>= 1) { sumL += __shfl_down_sync(0xffffffffu, sumL, o); sumL2 += __shfl_down_sync(0xffffffffu, sumL2, o); }
-    uint32_t is_last = 0;
-    if (lane == 0) {
-        atomicAdd((unsigned long long *)&P.rec[f].lap_sum, (unsigned long long)sumL);
-        atomicAdd((unsigned long long *)&P.rec[f].lap_sumsq, (unsigned long long)sumL2);
+    if (PAIR) {
+        // a warp may hold strips of both frames: one reduction per frame
+        long long a0 = half ? 0 : sumL, a1 = half ? 0 : sumL2, b0 = half ? sumL : 0, b1 = half ? sumL2 : 0;
+        for (int o = 16; o; o >>= 1) {
+            a0 += __shfl_down_sync(0xffffffffu, a0, o); a1 += __shfl_down_sync(0xffffffffu, a1, o);
+            b0 += __shfl_down_sync(0xffffffffu, b0, o); b1 += __shfl_down_sync(0xffffffffu, b1, o);
+        }
+        if (lane == 0) {
+            const int fa = 2 * (int)blockIdx.y;
+            if (a0 | a1) {
+                atomicAdd((unsigned long long *)&P.rec[fa].lap_sum, (unsigned long long)a0);
+                atomicAdd((unsigned long long *)&P.rec[fa].lap_sumsq, (unsigned long long)a1);
+            }
+            if (have2 && (b0 | b1)) {
+                atomicAdd((unsigned long long *)&P.rec[fa + 1].lap_sum, (unsigned long long)b0);
+                atomicAdd((unsigned long long *)&P.rec[fa + 1].lap_sumsq, (unsigned long long)b1);
+            }
+        }
+    } else {
+        for (int o = 16; o; o >>= 1) { sumL += __shfl_down_sync(0xffffffffu, sumL, o); sumL2 += __shfl_down_sync(0xffffffffu, sumL2, o); }
+        if (lane == 0) {
+            atomicAdd((unsigned long long *)&P.rec[f].lap_sum, (unsigned long long)sumL);
+            atomicAdd((unsigned long long *)&P.rec[f].lap_sumsq, (unsigned long long)sumL2);
+        }
     }
+    uint32_t is_last = 0;
     __syncwarp();
     if (lane == 0) {
         uint32_t old;
@@ -554,45 +587,55 @@ __global__ void __launch_bounds__(MAXT, MINB) k1_fused_kernel(K1Params P)
     is_last = __shfl_sync(0xffffffffu, is_last, 0);
     if (!is_last) return;
 
-    // ---- this warp is the last one of the band: the staged thumbnail rows (contiguous in the thumbnail) go out ----
-    if ((TM != 0)) {
-        const int ty0 = tab->thumb_row_begin[b], nty = tab->thumb_row_begin[b + 1] - ty0;
-        const uint4 *src = (const uint4 *)(smem + HDR + NRS * P.row_bytes + 64 + SLOT * nthr + 64);
-        uint4 *dst = (uint4 *)(P.thumbs + ((size_t)f * AVD_T + ty0) * AVD_T);
-        for (int i = lane; i < nty * (AVD_T / 16); i += 32) dst[i] = src[i];
-    }
-    // ---- INTER_AREA destination row b, column `lane` ----
-    const int M = cellM[lane];
-    uint32_t out;
-    bool close = false;
-    if (tab->area_int) {
-        out = sat_rne(__fmul_rn((float)(M >> 5), tab->inv_area));
-    } else {
-        // exact mean v = M / (H*sx).  close <=> |frac(v) - 0.5| <= 17/16 (sx+n+5) 2^-24 v, all in integers (times 2 H sx)
-        const uint32_t Dn = (uint32_t)H * (uint32_t)sx;
-        const uint32_t k = (uint32_t)M / Dn, r = (uint32_t)M - k * Dn;
-        const int d2 = (int)(2u * r) - (int)Dn;
-        const uint32_t bound = (uint32_t)(((unsigned long long)(uint32_t)M * (uint32_t)(17 * (sx + n + 5))) >> 27) + 2u;
-        close = (uint32_t)abs(d2) <= bound;
-        out = k + (d2 >= 0 ? 1u : 0u);
-    }
-    P.area32[(size_t)f * 1024 + b * 32 + lane] = (uint8_t)out;
-    // uncertified cells go to a list; k1_hash_finalize recomputes them in the library's float32 order
-    const uint32_t mask = __ballot_sync(0xffffffffu, close);
-    if (mask) {
-        uint32_t base = 0;
-        if (lane == 0) base = atomicAdd(P.fixlist, (uint32_t)__popc(mask));
-        base = __shfl_sync(0xffffffffu, base, 0);
-        if (close) P.fixlist[1 + base + __popc(mask & ((1u << lane) - 1u))] = (uint32_t)(P.frame0 + f) * 1024u + (uint32_t)(b * 32 + lane);
+    // ---- this warp is the last one of the band: per frame of the CTA, the staged thumbnail rows (contiguous in the thumbnail)
+    // go out, then INTER_AREA destination row b, column `lane` ----
+    for (int h = 0; h < (have2 ? 2 : 1); h++) {
+        const int fh = PAIR ? 2 * (int)blockIdx.y + h : f;
+        if ((TM != 0)) {
+            const int ty0 = tab->thumb_row_begin[b], nty = tab->thumb_row_begin[b + 1] - ty0;
+            const uint4 *src = (const uint4 *)(smem + HDR + NRS * stride + 64 + SLOT * nthr + 64 + h * MAX_TROWS * AVD_T);
+            uint4 *dst = (uint4 *)(P.thumbs + ((size_t)fh * AVD_T + ty0) * AVD_T);
+            for (int i = lane; i < nty * (AVD_T / 16); i += 32) dst[i] = src[i];
+        }
+        const int M = cellM[32 * h + lane];
+        uint32_t out;
+        bool close = false;
+        if (tab->area_int) {
+            out = sat_rne(__fmul_rn((float)(M >> 5), tab->inv_area));
+        } else {
+            // exact mean v = M / (H*sx).  close <=> |frac(v) - 0.5| <= 17/16 (sx+n+5) 2^-24 v, all in integers (times 2 H sx)
+            const uint32_t Dn = (uint32_t)H * (uint32_t)sx;
+            const uint32_t k = (uint32_t)M / Dn, r = (uint32_t)M - k * Dn;
+            const int d2 = (int)(2u * r) - (int)Dn;
+            const uint32_t bound = (uint32_t)(((unsigned long long)(uint32_t)M * (uint32_t)(17 * (sx + n + 5))) >> 27) + 2u;
+            close = (uint32_t)abs(d2) <= bound;
+            out = k + (d2 >= 0 ? 1u : 0u);
+        }
+        P.area32[(size_t)fh * 1024 + b * 32 + lane] = (uint8_t)out;
+        // uncertified cells go to a list; k1_hash_finalize recomputes them in the library's float32 order
+        const uint32_t mask = __ballot_sync(0xffffffffu, close);
+        if (mask) {
+            uint32_t base = 0;
+            if (lane == 0) base = atomicAdd(P.fixlist, (uint32_t)__popc(mask));
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (close) P.fixlist[1 + base + __popc(mask & ((1u << lane) - 1u))] = (uint32_t)(P.frame0 + fh) * 1024u + (uint32_t)(b * 32 + lane);
+        }
     }
 }
 
 }  // namespace
 
+// frames a CTA takes side by side: two where that fills the warps (W = 1280: 80 strips per frame)
+static int k1_frames_per_cta(int W)
+{
+    static const bool off = getenv("AVD_K1_NOPAIR") && atoi(getenv("AVD_K1_NOPAIR"));
+    return (W == 1280 && !off) ? 2 : 1;
+}
 static size_t k1_smem_bytes(int W)
 {
-    const int nthr = (W / 16 + 31) / 32 * 32;
-    return HDR + (size_t)NRS * 3 * W + 64 + (size_t)SLOT * nthr + 64 + (size_t)MAX_TROWS * AVD_T;
+    const int fpc = k1_frames_per_cta(W);
+    const int nthr = (fpc * (W / 16) + 31) / 32 * 32;
+    return HDR + (size_t)NRS * 3 * W * fpc + 64 + (size_t)SLOT * nthr + 64 + (size_t)MAX_TROWS * AVD_T * fpc;
 }
 
 bool k1_fused_supported(int H, int W, size_t pitch, size_t fstride, const void *base, const ShapeTables *htab)
@@ -610,22 +653,22 @@ bool k1_fused_supported(int H, int W, size_t pitch, size_t fstride, const void *
     return true;
 }
 
-template <int MAXT, int MINB, int JT, int TM>
+template <int MAXT, int MINB, int JT, int TM, bool PAIR = false>
 static int k1_launch(avd_ctx *ctx, const K1Params &P, int n, size_t smem, int threads, cudaStream_t st)
 {
     static size_t smem_set[64] = {};                 // per device: function attributes belong to the device's context
     size_t &set = smem_set[ctx->device & 63];
     if (smem > set) {
-        AVD_CUDA(ctx, cudaFuncSetAttribute(k1_fused_kernel<MAXT, MINB, JT, TM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        AVD_CUDA(ctx, cudaFuncSetAttribute(k1_fused_kernel<MAXT, MINB, JT, TM, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         set = smem;
     }
-    for (int f0 = 0; f0 < n; f0 += 65535) {                          // grid.y limit
-        int nb = n - f0 < 65535 ? n - f0 : 65535;
+    for (int f0 = 0; f0 < n; f0 += 65534) {                          // grid.y limit (even, so that pairs never straddle launches)
+        int nb = n - f0 < 65534 ? n - f0 : 65534;
         K1Params Q = P;
         Q.bgr = P.bgr + (size_t)f0 * P.fstride; Q.rec = P.rec + f0;
         Q.thumbs = P.thumbs + (size_t)f0 * AVD_T * AVD_T; Q.area32 = P.area32 + (size_t)f0 * 1024;
-        Q.frame0 = f0;
-        AVD_LAUNCH(ctx, "k1_fused", st, (k1_fused_kernel<MAXT, MINB, JT, TM><<<dim3(AVD_D, nb), threads, smem, st>>>(Q)));
+        Q.frame0 = f0; Q.nframes = nb;
+        AVD_LAUNCH(ctx, "k1_fused", st, (k1_fused_kernel<MAXT, MINB, JT, TM, PAIR><<<dim3(AVD_D, PAIR ? (nb + 1) / 2 : nb), threads, smem, st>>>(Q)));
     }
     return AVD_OK;
 }
@@ -638,13 +681,15 @@ int k1_fused(avd_ctx *ctx, const uint8_t *d_bgr, int n, int H, int W, size_t pit
     P.bgr = d_bgr; P.pitch = pitch; P.fstride = fstride; P.H = H; P.W = W; P.row_bytes = 3 * W;
     P.tab = tab; P.rec = d_rec; P.thumbs = d_thumbs; P.area32 = d_area32; P.fixlist = d_fixlist;
     const size_t smem = k1_smem_bytes(W);
-    const int threads = (W / 16 + 31) / 32 * 32;
+    const int fpc = k1_frames_per_cta(W);
+    const int threads = (fpc * (W / 16) + 31) / 32 * 32;
     const int jt = htab->strip_ntx_max;
     // pair-sum thumbnail: every horizontal tap pair is (1024, 1024) and all left taps have the same parity
     bool pair = true;
     for (int i = 0; i < AVD_T; i++)
         if (htab->lx[i].a0 != 1024 || htab->lx[i].a1 != 1024 || ((htab->lx[i].i0 ^ htab->lx[0].i0) & 1) ||
             htab->ly[i].a0 + htab->ly[i].a1 != 2048) pair = false;
+    if (fpc == 2 && pair) return k1_launch<160, 3, 4, 4, true>(ctx, P, n, smem, threads, st);      // W = 1280: two frames per CTA
     if (threads <= 128) {                                            // <= 2048 px wide
         if (pair) {
             if (W == 1280) return k1_launch<128, K1_MINB, 4, 4>(ctx, P, n, smem, threads, st);

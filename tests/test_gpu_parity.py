@@ -156,6 +156,22 @@ def test_area_rounding_boundaries(torch, eng, oracle):
     assert outs[0][0] == outs[1][0] and np.array_equal(outs[0][1], outs[1][1])
 
 
+def test_streaming_kernel_two_frames_per_cta(synth, torch, eng):
+    """W = 1280: a CTA of the streaming kernel takes band b of two consecutive frames side by side (80 strips per frame fill
+    2.5 warps).  Odd and even frame counts (the last CTA row holds one frame), integer and fractional INTER_AREA rows."""
+    for H in (720, 641, 960):
+        clip = synth.Clip(40, H, 1280, seed=7, events=True)
+        for n in (1, 3, 8):
+            fr = torch.from_numpy(np.stack([clip[i] for i in (0, 3, 12, 13, 20, 25, 31, 39)[:n]])).cuda()
+            outs = []
+            for mode in (0, 1):
+                eng.set_k1_mode(mode)
+                rec, th, ar = eng.frames_features(fr, want_area32=True)
+                outs.append((rec.cpu().numpy().tobytes(), th.cpu().numpy().tobytes(), ar.cpu().numpy().tobytes()))
+            eng.set_k1_mode(0)
+            assert outs[0] == outs[1], (H, n)
+
+
 def test_any_width_kernel_area_rounding_boundaries(torch, eng, oracle):
     """k1_rows.cu computes INTER_AREA cells as exact integers and lists the cells whose mean is within the float32 summation
     error of a rounding boundary for area_fix_kernel (the library's order): frames built so that many / all cells sit on or
