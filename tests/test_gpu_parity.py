@@ -404,11 +404,13 @@ def test_edge_cases_and_errors(torch, eng):
     assert len(eng.analyze_host([np.zeros((40, 50, 3), np.uint8)])) == 1   # engine still usable after errors
 
 
-def test_device_path_graph_replay_equals_plain_launches(synth, torch, eng):
+@pytest.mark.parametrize("H,W", [(720, 1280), (480, 854)])
+def test_device_path_graph_replay_equals_plain_launches(synth, torch, eng, H, W):
     """Engine.analyze_device_graph (CUDA graph of the step's launches) must return the same records as the plain
     launches, on first use (capture) and on replays with new frame contents at the same addresses, with and
-    without a chunk halo."""
-    clip = synth.Clip(40, 720, 1280, seed=21, events=True)
+    without a chunk halo; through the streaming kernel (two frames per CTA at this width) and the any-width kernel
+    (both append to the fix list inside the captured graph)."""
+    clip = synth.Clip(40, H, W, seed=21, events=True)
     frames = torch.from_numpy(np.stack([clip[i] for i in range(0, 40, 4)])).cuda()
     halo = torch.from_numpy(clip[39]).cuda()
     for prev in (None, halo):
