@@ -21,6 +21,7 @@
 // Arithmetic per value is that of k1_generic.cu (which stays as the on-device cross-check and the fallback for bands that do
 // not fit in shared memory): results are identical by construction and checked byte for byte in the tests.
 #include "avd_internal.h"
+#include <stdlib.h>
 
 namespace {
 
@@ -139,13 +140,14 @@ __device__ __forceinline__ void lap_chunk(const uint8_t *col, int GP, int qa, in
     }
 }
 
-#ifndef KR_MINB
-#define KR_MINB 3
-#endif
+// Two builds of the kernel.  PF (bands that leave room for three CTAs per SM at most): a thread's next group is loaded while it
+// converts the current one, 79 registers.  !PF (small bands: 480p-class frames and below): no load prefetch, 64 registers, four
+// CTAs per SM -- measured: 854x480 32.5 -> 33.9 %, 960x540 37 -> 40 %, 640x360 23 -> 25 %; 1918x1080 the other way round (45 against 36 %).
 constexpr int KR_MAXQ = 136;           // sequence rows of a band (H / 32 + 3, H <= 4096)
 constexpr int KR_MAXCH = 64;           // row chunks per strip
 
-__global__ void __launch_bounds__(KR_THREADS, KR_MINB) k1_rows_kernel(KRParams P)
+template <bool PF>
+__global__ void __launch_bounds__(KR_THREADS, PF ? 3 : 4) k1_rows_kernel(KRParams P)
 {
     extern __shared__ __align__(16) uint8_t sm[];
     const ShapeTables *__restrict__ tab = P.tab;
@@ -232,16 +234,24 @@ __global__ void __launch_bounds__(KR_THREADS, KR_MINB) k1_rows_kernel(KRParams P
         if (tid <= nchunk) qtab[tid] = 1 + (tid * n) / nchunk;
         for (int k = tid; k < 8 * ng; k += KR_THREADS) CS[k] = 0u;
         hx = tab->lx[tid];                                          // column tid; columns 256..319 are reloaded in their own pass
-        while (i < nitems) {
-            int j = i + KR_THREADS;
-            if (j < nitems) issue(j, B);
-            convert(A);
-            i = j;
-            if (i >= nitems) break;
-            j = i + KR_THREADS;
-            if (j < nitems) issue(j, A);
-            convert(B);
-            i = j;
+        if constexpr (PF) {
+            while (i < nitems) {
+                int j = i + KR_THREADS;
+                if (j < nitems) issue(j, B);
+                convert(A);
+                i = j;
+                if (i >= nitems) break;
+                j = i + KR_THREADS;
+                if (j < nitems) issue(j, A);
+                convert(B);
+                i = j;
+            }
+        } else {
+            while (i < nitems) {
+                convert(A);
+                i += KR_THREADS;
+                if (i < nitems) issue(i, A);
+            }
         }
     }
     __syncthreads();
@@ -454,10 +464,14 @@ int k1_rows(avd_ctx *ctx, const uint8_t *d_bgr, int n, int H, int W, size_t pitc
     P.tab = tab; P.rec = d_rec; P.thumbs = d_thumbs; P.area32 = d_area32; P.fixlist = d_fixlist;
     for (int b = 0; b <= AVD_D; b++) { P.own[b] = (unsigned short)htab->row_owner_begin[b]; P.tyb[b] = (unsigned short)htab->thumb_row_begin[b]; }
     const size_t smem = kr_smem_bytes(W, htab);
-    static size_t smem_set[64] = {};
-    size_t &set = smem_set[ctx->device & 63];
+    // four CTAs per SM fit (shared memory): the 64-register build without load prefetch
+    static const int pf_env = getenv("AVD_KR_PF") ? atoi(getenv("AVD_KR_PF")) : -1;
+    const bool pf = pf_env >= 0 ? pf_env != 0 : (smem + 2048) * 4 > 227 * 1024;
+    static size_t smem_set[2][64] = {};
+    size_t &set = smem_set[pf][ctx->device & 63];
     if (smem > set) {
-        AVD_CUDA(ctx, cudaFuncSetAttribute(k1_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        if (pf) AVD_CUDA(ctx, cudaFuncSetAttribute(k1_rows_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        else AVD_CUDA(ctx, cudaFuncSetAttribute(k1_rows_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         set = smem;
     }
     for (int f0 = 0; f0 < n; f0 += 65535) {
@@ -466,7 +480,8 @@ int k1_rows(avd_ctx *ctx, const uint8_t *d_bgr, int n, int H, int W, size_t pitc
         Q.bgr = P.bgr + (size_t)f0 * fstride; Q.rec = P.rec + f0;
         Q.thumbs = P.thumbs + (size_t)f0 * AVD_T * AVD_T; Q.area32 = P.area32 + (size_t)f0 * 1024;
         Q.frame0 = f0;
-        AVD_LAUNCH(ctx, "k1_rows", st, k1_rows_kernel<<<dim3(AVD_D, nb), KR_THREADS, smem, st>>>(Q));
+        if (pf) AVD_LAUNCH(ctx, "k1_rows", st, k1_rows_kernel<true><<<dim3(AVD_D, nb), KR_THREADS, smem, st>>>(Q));
+        else AVD_LAUNCH(ctx, "k1_rows", st, k1_rows_kernel<false><<<dim3(AVD_D, nb), KR_THREADS, smem, st>>>(Q));
     }
     return AVD_OK;
 }
