@@ -504,7 +504,10 @@ static int analyze_host_impl(avd_ctx *ctx, const uint8_t *const *h_frames, int n
         if (!yuv) AVD_CUDA(ctx, cudaEventRecord(ctx->ev_free[slot], ctx->compute));
         const int ready = f0 + nb, last = ready == n;
         const int pending = ready - k2_done - (k2_done == 0 ? 1 : 0);            // pairs not yet issued
-        if (pending > 0 && (last || pending >= k2_min)) {
+        // the batch issued after the LAST copy is the pipeline's un-hideable tail: flush before it, so that it only holds the
+        // last slot's pairs (120 samples of 1080p: 24 pairs = 0.45 ms -> 8 pairs = 0.3 ms after the last copy)
+        const bool before_last = !last && n - ready <= per_slot && pending >= 8;
+        if (pending > 0 && (last || pending >= k2_min || before_last)) {
             const uint8_t *t0 = ctx->thumbs + (size_t)k2_done * AVD_T * AVD_T;
             if ((rc = avd_flow_stats(ctx, t0, ready - k2_done, k2_done > 0 ? t0 - (size_t)AVD_T * AVD_T : nullptr, ctx->recs + k2_done, ctx->compute))) return rc;
             k2_done = ready;
