@@ -228,6 +228,10 @@ void avd_destroy(avd_ctx *ctx)
     for (void *h : ctx->host_allocs) cudaFreeHost(h);
     ctx->host_allocs.clear();
     for (int i = 0; i < 4; i++) { cudaEventDestroy(ctx->ev_copied[i]); cudaEventDestroy(ctx->ev_free[i]); }
+    if (ctx->k2_img) {
+        cudaStreamDestroy(ctx->k2_img);
+        for (int i = 0; i < 5; i++) cudaEventDestroy(ctx->k2_img_ev[i]);
+    }
     if (ctx->k2_side[0]) {
         for (int i = 0; i < 3; i++) cudaStreamDestroy(ctx->k2_side[i]);
         for (int i = 0; i < 6; i++) cudaEventDestroy(ctx->k2_ev[i]);

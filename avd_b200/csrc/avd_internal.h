@@ -68,6 +68,7 @@ struct avd_ctx {
     // K2 workspace (see k2_flow.cu)
     void *k2_ws = nullptr; size_t k2_ws_cap = 0; int k2_batch = 0;
     cudaStream_t k2_side[3] = {}; cudaEvent_t k2_ev[6] = {};     // further chains of a split batch (AVD_K2_SPLIT)
+    cudaStream_t k2_img = nullptr; cudaEvent_t k2_img_ev[5] = {};  // pyramid + polynomial expansion of the finer levels beside the coarse flow levels
     // host streaming ring (avd_analyze_host)
     uint8_t *ring = nullptr; size_t ring_cap = 0;
     uint8_t *bgr_slot = nullptr; size_t bgr_slot_cap = 0;   // YUV input: the converted frames of the slot in flight

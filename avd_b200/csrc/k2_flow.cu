@@ -520,6 +520,7 @@ struct ChainArgs {
     double *tile_stats;
     int mode;
     bool want_stats;
+    const cudaEvent_t *level_ready;     // level_ready[k] != nullptr: the polynomial expansion of level k runs on another stream
 };
 
 // The flow iterations of pairs [q0, q0 + nq) of the batch on stream st: levels 3..0, per level the update matrices
@@ -541,6 +542,7 @@ static int run_chain(avd_ctx *ctx, cudaStream_t st, const ChainArgs &A, int q0, 
     for (int k = 3; k >= 0; k--) {
         const int s = lvl_size(k);
         const int seg = seg_rows[k];
+        if (A.level_ready && A.level_ready[k]) AVD_CUDA(ctx, cudaStreamWaitEvent(st, A.level_ready[k], 0));
         dim3 gu((s + 31) / 32, (s + 7) / 8, nq), bu(32, 8);
         const int tasks = bx_strips(s) * bx_segs(s, seg) * nq;
 #define UM_LAUNCH(K, SRC, FLOW, COARSE) AVD_LAUNCH(ctx, (lvl_names ? um_name[K] : "update_matrices"), st, um_kernel<K, SRC><<<gu, bu, 0, st>>>(R, FLOW, COARSE, M, mode, q0))
@@ -604,23 +606,40 @@ int k2_flow(avd_ctx *ctx, const uint8_t *d_prev, const uint8_t *d_next, size_t p
             src.mode = 2; src.a = d_prev + (size_t)p0 * prev_stride; src.b = d_next + (size_t)p0 * next_stride;
             src.sa = prev_stride; src.sb = next_stride; mode = 2;
         }
-        AVD_LAUNCH(ctx, "pyr", st, pyr_kernel<3><<<dim3(40 / PYR_CW, ni), 256, 0, st>>>(src, pyr));
-        AVD_LAUNCH(ctx, "pyr", st, pyr_kernel<2><<<dim3(80 / PYR_CW, ni), 256, 0, st>>>(src, pyr));
-        AVD_LAUNCH(ctx, "pyr", st, pyr_kernel<1><<<dim3(160 / PYR_CW, ni), 256, 0, st>>>(src, pyr));
-        AVD_LAUNCH(ctx, "pyr", st, pyr_kernel<0><<<dim3(320 / PYR_CW, ni), 256, 0, st>>>(src, pyr));
-        for (int k = 3; k >= 0; k--) {
-            int s = lvl_size(k);
-#define PE_LAUNCH(K) AVD_LAUNCH(ctx, "polyexp", st, polyexp_kernel<K><<<dim3(s / PE_ROWS, ni), (s + 31) / 32 * 32, 3 * PE_ROWS * (s + 2 * PE_HALO) * sizeof(float), st>>>(pyr, R))
-            if (k == 3) PE_LAUNCH(3); else if (k == 2) PE_LAUNCH(2); else if (k == 1) PE_LAUNCH(1); else PE_LAUNCH(0);
-#undef PE_LAUNCH
+        // Per image: pyramid level k, then its polynomial expansion.  The flow chain starts at the coarsest level and its first
+        // levels are small, latency-bound launches, so only level 3 is prepared in front of it; levels 2, 1, 0 (three quarters of
+        // the per-image work) run on a side stream beside the chain's coarse levels, which waits for level k right before it
+        // needs it (AVD_K2_IMG_OVERLAP=0: everything in front, as before).  Same kernels, same arithmetic.
+        static const bool img_overlap = !(getenv("AVD_K2_IMG_OVERLAP") && !atoi(getenv("AVD_K2_IMG_OVERLAP")));
+        if (img_overlap && !ctx->k2_img) {
+            AVD_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->k2_img, cudaStreamNonBlocking));
+            for (int i = 0; i < 5; i++) AVD_CUDA(ctx, cudaEventCreateWithFlags(&ctx->k2_img_ev[i], cudaEventDisableTiming));
         }
+        cudaEvent_t level_ready[4] = {nullptr, nullptr, nullptr, nullptr};
+#define PYR_LAUNCH(K, S_) AVD_LAUNCH(ctx, "pyr", S_, pyr_kernel<K><<<dim3(lvl_size(K) / PYR_CW, ni), 256, 0, S_>>>(src, pyr))
+#define PE_LAUNCH(K, S_) AVD_LAUNCH(ctx, "polyexp", S_, polyexp_kernel<K><<<dim3(lvl_size(K) / PE_ROWS, ni), (lvl_size(K) + 31) / 32 * 32, 3 * PE_ROWS * (lvl_size(K) + 2 * PE_HALO) * sizeof(float), S_>>>(pyr, R))
+        if (img_overlap) {
+            cudaStream_t is = ctx->k2_img;
+            AVD_CUDA(ctx, cudaEventRecord(ctx->k2_img_ev[4], st));                // the thumbnails (and the workspace) are ready
+            AVD_CUDA(ctx, cudaStreamWaitEvent(is, ctx->k2_img_ev[4], 0));
+            PYR_LAUNCH(3, st); PE_LAUNCH(3, st);
+            PYR_LAUNCH(2, is); PE_LAUNCH(2, is); AVD_CUDA(ctx, cudaEventRecord(ctx->k2_img_ev[2], is));
+            PYR_LAUNCH(1, is); PE_LAUNCH(1, is); AVD_CUDA(ctx, cudaEventRecord(ctx->k2_img_ev[1], is));
+            PYR_LAUNCH(0, is); PE_LAUNCH(0, is); AVD_CUDA(ctx, cudaEventRecord(ctx->k2_img_ev[0], is));
+            for (int k = 0; k < 3; k++) level_ready[k] = ctx->k2_img_ev[k];
+        } else {
+            PYR_LAUNCH(3, st); PYR_LAUNCH(2, st); PYR_LAUNCH(1, st); PYR_LAUNCH(0, st);
+            PE_LAUNCH(3, st); PE_LAUNCH(2, st); PE_LAUNCH(1, st); PE_LAUNCH(0, st);
+        }
+#undef PYR_LAUNCH
+#undef PE_LAUNCH
         // Flow iterations (run_chain): um_kernel<K,.> + box_cs_kernel<K,.> per level, 3 iterations each.
         // AVD_K2_SPLIT=2: the pairs of the batch are split into two halves whose chains run on two streams, the second one
         // launch behind the first, so that the memory-bound update_matrices of one half shares the SMs with the issue-bound
         // box_solve of the other.  A pair's arithmetic does not depend on which half it is in.
         static const int split_env = getenv("AVD_K2_SPLIT") ? atoi(getenv("AVD_K2_SPLIT")) : 2;
         const int split = split_env < 1 ? 1 : (split_env > 4 ? 4 : split_env);
-        ChainArgs A{R, M, flowA, flowB, tile_stats, mode, d_rec_first != nullptr};
+        ChainArgs A{R, M, flowA, flowB, tile_stats, mode, d_rec_first != nullptr, level_ready};
         if (split >= 2 && np >= 16 * split) {      // measured: 119 pairs 1.52 -> 1.45 ms, 80: 1.08 -> 1.03, 40: 0.64 -> 0.63, 16: slower
             if (!ctx->k2_side[0]) {
                 for (int i = 0; i < 3; i++) AVD_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->k2_side[i], cudaStreamNonBlocking));
