@@ -302,30 +302,48 @@ __device__ __forceinline__ void um_pixel_c(const float *__restrict__ R0, const f
     m[4] = r6 * r2 + r5 * r3;
 }
 
+#ifndef UM_PPT
+#define UM_PPT 2      /* pixels per thread (rows y and y + 8 of a 32 x 16 block): more loads in flight per warp, -1 % on the pass */
+#endif
 template <int K, int FLOWSRC>
 __global__ void __launch_bounds__(256) um_kernel(const float *__restrict__ Rall, const float *__restrict__ flow, const float *__restrict__ coarse,
                                                  float *__restrict__ Mall, int pair_img_mode, int p_base)
 {
     constexpr int S = lvl_size(K), plane = S * S;
-    const int x = blockIdx.x * 32 + threadIdx.x, y = blockIdx.y * 8 + threadIdx.y, p = blockIdx.z + p_base;
-    if (x >= S || y >= S) return;
+    const int x = blockIdx.x * 32 + threadIdx.x, p = blockIdx.z + p_base;
+    if (x >= S) return;
     const int ia = pair_img_mode == 2 ? 2 * p : p;
-    const int o = y * S + x;
     const float *R0 = Rall + (size_t)ia * PYR_PX * 5 + lvl_off(K) * 5;
     const float *R1 = R0 + (size_t)PYR_PX * 5;
-    float dx = 0.f, dy = 0.f;
-    if (FLOWSRC == 1) {
-        const float *f = flow + (size_t)blockIdx.z * 2 * plane + o;      // flow buffers are indexed by the pair's position in its chain
-        dx = f[0]; dy = f[plane];
-    } else if (FLOWSRC == 2) {
-        constexpr int cs = S >> 1;
-        const float *cf = coarse + (size_t)blockIdx.z * 2 * cs * cs;
-        dx = up2_sample(cf, cs, x, y); dy = up2_sample(cf + cs * cs, cs, x, y);
+    int ys[UM_PPT];
+    float dx[UM_PPT], dy[UM_PPT];
+#pragma unroll
+    for (int i = 0; i < UM_PPT; i++) {
+        const int y = blockIdx.y * 8 * UM_PPT + threadIdx.y + 8 * i;
+        ys[i] = y;
+        dx[i] = dy[i] = 0.f;
+        if (y < S) {
+            const int o = y * S + x;
+            if (FLOWSRC == 1) {
+                const float *f = flow + (size_t)blockIdx.z * 2 * plane + o;      // flow buffers are indexed by the pair's position in its chain
+                dx[i] = f[0]; dy[i] = f[plane];
+            } else if (FLOWSRC == 2) {
+                constexpr int cs = S >> 1;
+                const float *cf = coarse + (size_t)blockIdx.z * 2 * cs * cs;
+                dx[i] = up2_sample(cf, cs, x, y); dy[i] = up2_sample(cf + cs * cs, cs, x, y);
+            }
+        }
     }
-    float m[5];
-    um_pixel_c<S>(R0, R1, x, y, dx, dy, m);
-    float *M = Mall + (size_t)blockIdx.z * 5 * T * T + o;      // M is indexed by the pair's position in the (sub-)batch
-    M[0] = m[0]; M[plane] = m[1]; M[2 * plane] = m[2]; M[3 * plane] = m[3]; M[4 * plane] = m[4];
+    float m[UM_PPT][5];
+#pragma unroll
+    for (int i = 0; i < UM_PPT; i++)
+        if (ys[i] < S) um_pixel_c<S>(R0, R1, x, ys[i], dx[i], dy[i], m[i]);
+#pragma unroll
+    for (int i = 0; i < UM_PPT; i++)
+        if (ys[i] < S) {
+            float *M = Mall + (size_t)blockIdx.z * 5 * T * T + ys[i] * S + x;      // M is indexed by the pair's position in the (sub-)batch
+            M[0] = m[i][0]; M[plane] = m[i][1]; M[2 * plane] = m[i][2]; M[3 * plane] = m[i][3]; M[4 * plane] = m[i][4];
+        }
 }
 
 // 15x15 box sums + 2x2 solve, one CHANNEL per warp.
@@ -543,7 +561,7 @@ static int run_chain(avd_ctx *ctx, cudaStream_t st, const ChainArgs &A, int q0, 
         const int s = lvl_size(k);
         const int seg = seg_rows[k];
         if (A.level_ready && A.level_ready[k]) AVD_CUDA(ctx, cudaStreamWaitEvent(st, A.level_ready[k], 0));
-        dim3 gu((s + 31) / 32, (s + 7) / 8, nq), bu(32, 8);
+        dim3 gu((s + 31) / 32, (s + 8 * UM_PPT - 1) / (8 * UM_PPT), nq), bu(32, 8);
         const int tasks = bx_strips(s) * bx_segs(s, seg) * nq;
 #define UM_LAUNCH(K, SRC, FLOW, COARSE) AVD_LAUNCH(ctx, (lvl_names ? um_name[K] : "update_matrices"), st, um_kernel<K, SRC><<<gu, bu, 0, st>>>(R, FLOW, COARSE, M, mode, q0))
 #define BOX_LAUNCH(K, STATS) AVD_LAUNCH(ctx, (lvl_names ? box_name[K] : "box_solve"), st, box_cs_kernel<K, STATS><<<tasks, BCS_THREADS, 0, st>>>(M, cur, seg, nq, STATS ? tile_stats : nullptr, q0))
