@@ -14,12 +14,15 @@
 //                                  squares through IDP (exact integers); columns >= W of the last strip are forced to L = 0
 //   thumbnail   video.py:43        11-bit fixed point INTER_LINEAR; a thread owns a thumbnail column (taps and weights in
 //                                  registers) and walks the thumbnail rows whose top tap row the band owns
-//   INTER_AREA  video.py:6         the library's float32 arithmetic in the library's ORDER: horizontal pass
-//                                  one thread per (row, cell column), sequential adds (bytes become floats through a byte
-//                                  permute into the mantissa of 2^23); vertical pass one thread per cell column.  Integer
-//                                  scales: exact block sums (IDP.4A over aligned words), one float multiply.
-// Arithmetic per value is that of k1_generic.cu (which stays as the on-device cross-check and the fallback for bands that do
-// not fit in shared memory): results are identical by construction and checked byte for byte in the tests.
+//   INTER_AREA  video.py:6         exact integer cell sums: the Laplacian march also accumulates the column sums of the owned
+//                                  rows; weighted by the fractional head / tail row they give V[x], and a cell is the sum
+//                                  of V over its columns with the fractional head / tail column (all weights in 1/32
+//                                  units, M = mean * W * H < 2^32).  The library's float32 result can differ from the exactly
+//                                  rounded mean only within its summation error of a rounding boundary: those cells are
+//                                  listed and recomputed in the library's ORDER by area_fix_kernel -- the
+//                                  certificate of k1_fused.cu, with both axes fractional.
+// Gray, Laplacian and thumbnail arithmetic per value is that of k1_generic.cu (which stays as the on-device cross-check and the
+// fallback for bands that do not fit in shared memory); results are checked byte for byte against it in the tests.
 #include "avd_internal.h"
 #include <stdlib.h>
 
