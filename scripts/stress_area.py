@@ -1,5 +1,6 @@
-"""Randomised stress of the INTER_AREA certificate + fix-up: streaming kernel vs the generic kernel (library order)
-on frames built to put many cell means next to rounding boundaries.  Prints mismatch counts (must be 0)."""
+"""Randomised stress of the INTER_AREA certificate + fix-up: streaming kernel (and, with `rows` as argv[1], the any-width
+kernel on ragged / fractional-scale shapes) vs the generic kernel (library order) on frames built to put many cell means next
+to rounding boundaries.  Prints mismatch counts (must be 0)."""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
@@ -7,9 +8,13 @@ from avd_b200.engine import Engine
 eng = Engine(0)
 g = torch.Generator(device="cuda"); g.manual_seed(7)
 bad = tot = flagged_like = 0
-for (H, W) in [(720, 1280), (1080, 1920), (2160, 3840), (648, 1344), (1000, 2048)]:
+ROWS = len(sys.argv) > 1 and sys.argv[1] == "rows"
+MODE = 3 if ROWS else 0
+SHAPES = [(480, 854), (768, 1366), (333, 777), (540, 960), (1080, 1918), (33, 35), (600, 1920), (97, 4001)] if ROWS else \
+         [(720, 1280), (1080, 1920), (2160, 3840), (648, 1344), (1000, 2048)]
+for (H, W) in SHAPES:
     for kind in range(8):
-        n = 24 if H < 2000 else 6
+        n = (96 if H * W < 600000 else 24) if H < 2000 else 6
         base = torch.randint(0, 255, (n, 1, 1, 1), device="cuda", generator=g).float()
         if kind == 0:   # two adjacent levels, random mix per frame: means spread over [v, v+1]
             pr = torch.rand((n, 1, 1, 1), device="cuda", generator=g)
@@ -32,7 +37,7 @@ for (H, W) in [(720, 1280), (1080, 1920), (2160, 3840), (648, 1344), (1000, 2048
                 .repeat_interleave(8, 1).repeat_interleave(8, 2)[:, :H, :W]
         fr = fr.clamp(0, 255).to(torch.uint8).expand(n, H, W, 3).contiguous()     # B=G=R=v -> gray = v
         outs = []
-        for mode in (0, 1):
+        for mode in (MODE, 1):
             eng.set_k1_mode(mode)
             rec, th, ar = eng.frames_features(fr, want_area32=True)
             outs.append((ar.clone(), th.clone(), rec.clone()))
