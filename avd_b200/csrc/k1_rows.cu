@@ -149,7 +149,9 @@ __device__ __forceinline__ void lap_chunk(const uint8_t *col, int GP, int qa, in
 constexpr int KR_MAXQ = 136;           // sequence rows of a band (H / 32 + 3, H <= 4096)
 constexpr int KR_MAXCH = 64;           // row chunks per strip
 
-template <bool PF>
+// AL: every row of the launch starts on a 16-byte boundary (16-byte aligned buffer, row pitch and frame stride: the upload ring
+// of the host path, dense frames whose width is a multiple of 16): three loads per group, no byte shift.
+template <bool PF, bool AL>
 __global__ void __launch_bounds__(KR_THREADS, PF ? 3 : 4) k1_rows_kernel(KRParams P)
 {
     extern __shared__ __align__(16) uint8_t sm[];
@@ -190,12 +192,17 @@ __global__ void __launch_bounds__(KR_THREADS, PF ? 3 : 4) k1_rows_kernel(KRParam
         auto issue = [&](int i, Item &it) {
             it.q = (int)__umulhi((uint32_t)i, P.magic); it.g = i - it.q * ng;
             const uint32_t off = (uint32_t)r101(own0 - 1 + it.q, H) * (uint32_t)P.pitch + 48u * (uint32_t)it.g;
-            it.mis = (base_lo + off) & 15u;
+            it.mis = AL ? 0u : (base_lo + off) & 15u;
             const uint4 *al = (const uint4 *)(frame + off - it.mis);
             const int nbytes = 3 * W - 48 * it.g;                     // bytes of the row from the group's first byte on (> 0)
             const int mis = (int)it.mis;
             const uint4 z = make_uint4(0u, 0u, 0u, 0u);
             it.c0 = al[0];
+            if (AL) {
+                it.c1 = (16 < nbytes) ? al[1] : z;
+                it.c2 = (32 < nbytes) ? al[2] : z;
+                return;
+            }
             it.c1 = (16 - mis < nbytes) ? al[1] : z;
             it.c2 = (32 - mis < nbytes) ? al[2] : z;
             it.c3 = (mis != 0 && 48 - mis < nbytes) ? al[3] : z;
@@ -204,12 +211,17 @@ __global__ void __launch_bounds__(KR_THREADS, PF ? 3 : 4) k1_rows_kernel(KRParam
             const uint32_t w[16] = {it.c0.x, it.c0.y, it.c0.z, it.c0.w, it.c1.x, it.c1.y, it.c1.z, it.c1.w,
                                     it.c2.x, it.c2.y, it.c2.z, it.c2.w, it.c3.x, it.c3.y, it.c3.z, it.c3.w};
             uint32_t v[12];
-            const uint32_t bs = 8u * (it.mis & 3u);
-            switch (it.mis >> 2) {
-            case 0: window_shift<0>(w, bs, v); break;
-            case 1: window_shift<1>(w, bs, v); break;
-            case 2: window_shift<2>(w, bs, v); break;
-            default: window_shift<3>(w, bs, v); break;
+            if (AL) {
+#pragma unroll
+                for (int k = 0; k < 12; k++) v[k] = w[k];
+            } else {
+                const uint32_t bs = 8u * (it.mis & 3u);
+                switch (it.mis >> 2) {
+                case 0: window_shift<0>(w, bs, v); break;
+                case 1: window_shift<1>(w, bs, v); break;
+                case 2: window_shift<2>(w, bs, v); break;
+                default: window_shift<3>(w, bs, v); break;
+                }
             }
             uint4 o;
             o.x = gray4(v[0], v[1], v[2]); o.y = gray4(v[3], v[4], v[5]); o.z = gray4(v[6], v[7], v[8]); o.w = gray4(v[9], v[10], v[11]);
@@ -470,11 +482,14 @@ int k1_rows(avd_ctx *ctx, const uint8_t *d_bgr, int n, int H, int W, size_t pitc
     // four CTAs per SM fit (shared memory): the 64-register build without load prefetch
     static const int pf_env = getenv("AVD_KR_PF") ? atoi(getenv("AVD_KR_PF")) : -1;
     const bool pf = pf_env >= 0 ? pf_env != 0 : (smem + 2048) * 4 > 227 * 1024;
-    static size_t smem_set[2][64] = {};
-    size_t &set = smem_set[pf][ctx->device & 63];
+    static const bool al_off = getenv("AVD_KR_NOALIGNED") && atoi(getenv("AVD_KR_NOALIGNED"));
+    // (only with the small-band build: with the prefetching build the aligned form measured slower, 1936x1080 46 against 52 %)
+    const bool al = !al_off && !pf && pitch % 16 == 0 && fstride % 16 == 0 && ((uintptr_t)d_bgr % 16) == 0;
+    void (*kern)(KRParams) = pf ? k1_rows_kernel<true, false> : (al ? k1_rows_kernel<false, true> : k1_rows_kernel<false, false>);
+    static size_t smem_set[4][64] = {};
+    size_t &set = smem_set[2 * pf + al][ctx->device & 63];
     if (smem > set) {
-        if (pf) AVD_CUDA(ctx, cudaFuncSetAttribute(k1_rows_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        else AVD_CUDA(ctx, cudaFuncSetAttribute(k1_rows_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        AVD_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         set = smem;
     }
     for (int f0 = 0; f0 < n; f0 += 65535) {
@@ -483,8 +498,7 @@ int k1_rows(avd_ctx *ctx, const uint8_t *d_bgr, int n, int H, int W, size_t pitc
         Q.bgr = P.bgr + (size_t)f0 * fstride; Q.rec = P.rec + f0;
         Q.thumbs = P.thumbs + (size_t)f0 * AVD_T * AVD_T; Q.area32 = P.area32 + (size_t)f0 * 1024;
         Q.frame0 = f0;
-        if (pf) AVD_LAUNCH(ctx, "k1_rows", st, k1_rows_kernel<true><<<dim3(AVD_D, nb), KR_THREADS, smem, st>>>(Q));
-        else AVD_LAUNCH(ctx, "k1_rows", st, k1_rows_kernel<false><<<dim3(AVD_D, nb), KR_THREADS, smem, st>>>(Q));
+        AVD_LAUNCH(ctx, "k1_rows", st, kern<<<dim3(AVD_D, nb), KR_THREADS, smem, st>>>(Q));
     }
     return AVD_OK;
 }
