@@ -172,6 +172,21 @@ def test_streaming_kernel_two_frames_per_cta(synth, torch, eng):
             assert outs[0] == outs[1], (H, n)
 
 
+def test_any_width_kernel_extreme_aspect_ratios(torch, eng):
+    """k1_rows.cu at the corners of its shape range: 128-row bands of two 16-pixel groups, one-row bands 4096 pixels wide,
+    widths one pixel off the streaming kernel's grid -- byte for byte the generic path."""
+    rng = np.random.default_rng(3)
+    for (H, W) in [(4096, 33), (35, 4096), (2048, 100), (720, 1281), (719, 1279), (32, 4096), (4096, 32)]:
+        fr = torch.from_numpy(rng.integers(0, 256, (3, H, W, 3), dtype=np.uint8)).cuda()
+        outs = []
+        for mode in (3, 1):
+            eng.set_k1_mode(mode)
+            rec, th, ar = eng.frames_features(fr, want_area32=True)
+            outs.append((rec.cpu().numpy().tobytes(), th.cpu().numpy().tobytes(), ar.cpu().numpy().tobytes()))
+        eng.set_k1_mode(0)
+        assert outs[0] == outs[1], (H, W)
+
+
 def test_any_width_kernel_area_rounding_boundaries(torch, eng, oracle):
     """k1_rows.cu computes INTER_AREA cells as exact integers and lists the cells whose mean is within the float32 summation
     error of a rounding boundary for area_fix_kernel (the library's order): frames built so that many / all cells sit on or
