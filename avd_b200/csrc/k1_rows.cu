@@ -319,8 +319,10 @@ __global__ void __launch_bounds__(KR_THREADS, PF ? 3 : 4) k1_rows_kernel(KRParam
         auto px = [&](const LinTap &h, int j) -> uint32_t {
             const int4 ri = trow[j];
             const uint8_t *r0 = Gx + ri.x, *r1 = Gx + ri.y;
-            const int S0 = r0[h.i0] * h.a0 + r0[h.i1] * h.a1;
-            const int S1 = r1[h.i0] * h.a0 + r1[h.i1] * h.a1;
+            // the right tap is column i0 + 1, except at the clamped right edge where its weight a1 is 0 (build_lin_taps):
+            // reading column i0 + 1 there (position W holds the reflected pixel) multiplies it by 0
+            const int S0 = r0[h.i0] * h.a0 + r0[h.i0 + 1] * h.a1;
+            const int S1 = r1[h.i0] * h.a0 + r1[h.i0 + 1] * h.a1;
             return (uint32_t)((((ri.z * (S0 >> 4)) >> 16) + ((ri.w * (S1 >> 4)) >> 16) + 2) >> 2);
         };
         auto px2 = [&](int tx, int j) -> uint32_t {                  // 640x640: the library's 2x2 mean
