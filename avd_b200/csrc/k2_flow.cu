@@ -185,8 +185,10 @@ __global__ void __launch_bounds__(T, PE_MINB) polyexp_kernel(const float *__rest
             for (int j = 1; j <= 5; j++) {
                 const float p0 = w[5 + e + j], m0 = w[5 + e - j];
                 const double tg = (double)(p0 + m0);
-                b1[e] += tg * (double)FC.g[j];
-                b4[e] += tg * (double)FC.xxg[j];
+                // tg and the coefficient are float values held in doubles: their product is exact (48 bits), so one fused
+                // multiply-add rounds exactly like the library's multiply followed by add
+                b1[e] = __fma_rn(tg, (double)FC.g[j], b1[e]);
+                b4[e] = __fma_rn(tg, (double)FC.xxg[j], b4[e]);
                 b2[e] += (double)((p0 - m0) * FC.xg[j]);
             }
         }
