@@ -208,10 +208,11 @@ long long avd_check_guards(avd_ctx *ctx);
 int avd_profile_enable(avd_ctx *ctx, int on);
 int avd_profile_read(avd_ctx *ctx, char *buf, size_t cap);
 
-/* Select the per-frame kernel: 0 = auto (streaming fused kernel when W % 64 == 0, 640 <= W,H <= 4096 and buffers
- * are 16-byte aligned; banded fused kernel when W % 16 == 0; any-width fused kernel when a band of gray rows fits in
- * shared memory; generic multi-kernel path otherwise), 1 = force the generic path, 2 = skip the streaming kernel,
- * 3 = skip the streaming and the banded kernel (any-width fused kernel, or generic).  For tests. */
+/* Select the per-frame kernel: 0 = auto (streaming fused kernel when W % 64 == 0, W >= 1280, 640 <= H <= 4096 and the
+ * buffers are 16-byte aligned; else the any-width fused kernel when a band of gray rows fits in shared memory; else the
+ * banded fused kernel when W % 16 == 0; generic multi-kernel path otherwise), 1 = force the generic path, 2 = the banded
+ * kernel where it applies (else any-width, else generic), 3 = the any-width kernel where it applies (else generic).
+ * All four produce identical bytes.  For tests. */
 int avd_set_k1_mode(avd_ctx *ctx, int mode);
 
 /*
